@@ -1,0 +1,441 @@
+#!/usr/bin/env python
+"""bench.py -- weight matrices spectrally analysed per second (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                 # this repo's CUDA path
+    python bench.py --impl reference --gpus 1 --steps 2 --warmup 1 # reference CPU algorithm
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W   # one rank per GPU
+
+Workload (config.workload): BASELINE.json configs[1], "Scenario A: ViT-Tiny 192d/6L":
+36 fp32 matrices per checkpoint (24x 192x192 as q/k/v row-blocks of a fused qkv buffer
++ proj, 6x 768x192, 6x 192x768), 31 epochs x 3 seeds = 93 checkpoints = 3348 matrices =
+987 MB per GPU per step (larger than the 126 MB L2, so every step re-reads HBM).
+One step = one pass of the hot path over that batch.  Weak scaling: every rank analyses
+its own 93 checkpoints, the only exchange is one NCCL gather of the 64-byte records.
+
+Printed keys: see the contract in the task description; `value` = device-resident
+throughput, `e2e` = same metric from pinned HOST buffers through the public API
+(`SweepRunner.run_host`: H2D copies + kernels + D2H of records and singular values in the
+timed region), `roofline` = the dominant kernel against its bound, `cpu_baseline` = the
+reference's algorithm (oracle port: 5 SciPy SVDs per matrix) timed on this box's cores.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+SCENARIO = {"name": "Scenario A: ViT-Tiny 192d/6L", "embed_dim": 192, "depth": 6, "epochs": 31, "seeds": (42, 142, 242)}
+FP64_PEAK_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 148 SM x 64 FP64 FMA/clk x 2 flop x 1.965 GHz
+
+
+# --------------------------------------------------------------------------- utils
+def load_peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        d["source"] = "measured (MEASURED_PEAKS.json)"
+        return d
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML)."""
+
+    REASONS = {
+        0x0000000000000004: "sw_power_cap",
+        0x0000000000000008: "hw_slowdown",
+        0x0000000000000020: "sw_thermal_slowdown",
+        0x0000000000000040: "hw_thermal_slowdown",
+        0x0000000000000080: "hw_power_brake_slowdown",
+    }
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self._nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+
+    def summary(self) -> dict:
+        import statistics
+
+        return {
+            "sm_mhz": statistics.median(self.samples) if self.samples else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+def physical_gpu_index(local: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except Exception:
+            return local
+    return local
+
+
+# ------------------------------------------------------------------- CPU reference
+def _cpu_worker_init():
+    """One BLAS thread per worker process.  Both OpenBLAS copies (NumPy's and SciPy's) must
+    be loaded before the limit is applied, or SciPy's keeps its default thread count and
+    the pool oversubscribes the cores."""
+    global _blas_limit
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    os.environ["OMP_NUM_THREADS"] = "1"
+    import numpy  # noqa: F401
+    import scipy.linalg  # noqa: F401
+    import scipy.stats  # noqa: F401
+    from threadpoolctl import threadpool_limits
+
+    _blas_limit = threadpool_limits(1)
+
+
+def _cpu_worker(w):
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import spectral_oracle as orc
+
+    out = orc.reference_cost_metrics(w)  # 4 metric SVDs + the driver's 5th SVD
+    return out["metrics"]["stable_rank"]
+
+
+def host_checkpoints(n_ckpt: int, seed0: int = 42):
+    """Synthetic Scenario-A checkpoints on the host (NumPy), the reference arm's input."""
+    import numpy as np
+
+    d, depth = SCENARIO["embed_dim"], SCENARIO["depth"]
+    out = []
+    for c in range(n_ckpt):
+        rng = np.random.default_rng(seed0 * 1_000_003 + c)
+        mats = []
+        for _ in range(depth):
+            qkv = (rng.standard_normal((3 * d, d)) * 0.02).astype(np.float32)
+            mats += [qkv[:d], qkv[d : 2 * d], qkv[2 * d :]]
+            mats += [(rng.standard_normal(s) * 0.02).astype(np.float32) for s in ((d, d), (4 * d, d), (d, 4 * d))]
+        out.append(mats)
+    return out
+
+
+def time_cpu_reference(n_ckpt: int, cores: int, pool=None) -> tuple[float, int]:
+    """Seconds to analyse n_ckpt checkpoints with the reference's algorithm on `cores`
+    processes x 1 BLAS thread (BASELINE.md "pool" mode).  Returns (seconds, matrices)."""
+    mats = [w for ck in host_checkpoints(n_ckpt) for w in ck]
+    own = pool is None
+    if own:
+        import multiprocessing as mp
+
+        pool = mp.get_context("fork").Pool(cores, initializer=_cpu_worker_init)
+        pool.map(_cpu_worker, mats[: min(len(mats), cores)])  # warm the workers
+    t0 = time.perf_counter()
+    pool.map(_cpu_worker, mats, chunksize=1)
+    dt = time.perf_counter() - t0
+    if own:
+        pool.close()
+        pool.join()
+    return dt, len(mats)
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args) -> None:
+    """`--impl reference`: the reference's own CPU algorithm for this path.  The reference
+    is pure Python over SciPy (nothing to compile into oracle/_ref), so this times the
+    oracle port -- same SciPy/LAPACK calls, 5 SVDs per matrix -- on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    cores = host_cores()
+    # bounded sample, but at least ~4 matrices per core so every core is kept busy
+    n_ckpt = max(1, args.ref_ckpts, -(-cores * 4 // 36))
+    pool = mp.get_context("fork").Pool(cores, initializer=_cpu_worker_init)
+    mats = [w for ck in host_checkpoints(n_ckpt) for w in ck]
+    times = []
+    for step in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, mats, chunksize=1)
+        dt = time.perf_counter() - t0
+        if step >= args.warmup:
+            times.append(dt)
+    pool.close()
+    pool.join()
+    total = sum(times)
+    value = len(mats) * len(times) / total
+    sample = f"{n_ckpt} Scenario-A checkpoints ({len(mats)} matrices) per step, {cores} processes x 1 BLAS thread"
+    line = {
+        "impl": "reference",
+        "metric": "weight matrices spectrally analysed/sec (ViT-Tiny Q/K/V/MLP)",
+        "value": value,
+        "unit": "matrices/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": SCENARIO["name"], "matrices_per_step": len(mats), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "matrices/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "matrices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------ GPU arm
+def run_b200_arm(args) -> None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import vision_spectra_b200 as pkg
+    from vision_spectra_b200.sweep import CheckpointLayout, SweepRunner, gather_records
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    lay = CheckpointLayout.vit(SCENARIO["embed_dim"], SCENARIO["depth"])
+    n_ckpt = args.ckpts
+    eng = pkg.SpectraEngine(dev)
+    runner = SweepRunner(eng, lay, ckpts_per_chunk=args.chunk)
+
+    # synthetic random-init weights, generated on the device
+    arenas = []
+    for c in range(n_ckpt):
+        seed = SCENARIO["seeds"][c % 3] * 1_000_003 + c // 3 + 1_000 * rank
+        g = torch.Generator(device=dev).manual_seed(seed)
+        arenas.append(torch.randn(lay.arena_elems, generator=g, device=dev, dtype=torch.float32) * 0.02)
+    matrices = n_ckpt * lay.matrices
+    in_bytes = n_ckpt * lay.bytes
+
+    def step_device():
+        res = runner.run_device(arenas, want_sv=True)
+        out = gather_records(res.records) if world > 1 else res.records
+        return res, out
+
+    def sync_all():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(dev)
+
+    # ---------------- device-resident throughput ("value")
+    for _ in range(args.warmup):
+        step_device()
+    sync_all()
+    eng.lib.vsp_reset_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(physical_gpu_index(local)) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            res, gathered = step_device()
+        e1.record()
+        sync_all()
+    launches = int(eng.lib.vsp_kernel_launch_count())
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lt := torch.tensor([launches], device=dev), op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    ms_total = float(ms.item())
+    value = world * matrices * args.steps / (ms_total / 1e3)
+
+    # sanity: every record of the last step is a finished, finite analysis
+    rec = res.records_host()
+    assert rec.shape[0] == matrices and int((rec["status"] != 0).sum()) == 0, "bench records not clean"
+    if rank == 0 and world > 1:
+        assert gathered.numel() == world * matrices * 64
+
+    # ---------------- per-stage timing (CUDA events between the kernels, same stream)
+    stage_acc = np.zeros(3)
+    reps = max(1, min(3, args.steps))
+    for _ in range(reps):
+        sm: list = []
+        runner.run_device(arenas, want_sv=True, stage_ms=sm)
+        stage_acc += np.array(sm)
+    stage_ms = stage_acc / reps
+    sync_all()
+
+    # ---------------- end to end from pinned host memory ("e2e")
+    host_arenas = [a.cpu().pin_memory() for a in arenas]
+    for _ in range(max(1, args.warmup // 2)):
+        runner.run_host(host_arenas, want_sv=True)
+    sync_all()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, args.steps // 2)
+    for _ in range(e2e_steps):
+        rec_h, sv_h = runner.run_host(host_arenas, want_sv=True)
+    torch.cuda.synchronize(dev)
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * matrices * e2e_steps / float(e2e_s.item())
+    d2h_bytes = rec_h.nbytes + (sv_h.nbytes if sv_h is not None else 0)
+    assert int((rec_h["status"] != 0).sum()) == 0
+    np.testing.assert_allclose(rec_h["metrics"], rec["metrics"], rtol=1e-12)  # same answers both ways
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel
+    peaks = load_peaks()
+    names = ["gram_f64_kernel", "tridiag_smem_kernel", "bisect_metrics_kernel"]
+    alg = {
+        "gram_f64_kernel": {"bound": "hbm", "work": in_bytes / 1e9, "unit": "GB/s", "peak": peaks["hbm_gbs"],
+                            "flops": n_ckpt * lay.flops_gram()},
+        "tridiag_smem_kernel": {"bound": "fp64", "work": n_ckpt * lay.flops_tridiag() / 1e12, "unit": "TFLOP/s",
+                                "peak": FP64_PEAK_TFLOPS},
+        "bisect_metrics_kernel": {"bound": "fp64", "work": None, "unit": "TFLOP/s", "peak": FP64_PEAK_TFLOPS},
+    }
+    stages = []
+    for nm, t in zip(names, stage_ms):
+        a = alg[nm]
+        ach = None if a["work"] is None else a["work"] / (t / 1e3)
+        stages.append({"kernel": nm, "ms": float(t), "share": float(t / stage_ms.sum()), "bound": a["bound"],
+                       "achieved": ach, "peak": a["peak"], "unit": a["unit"],
+                       "frac": None if ach is None else ach / a["peak"]})
+    dom = max((s for s in stages if s["achieved"] is not None), key=lambda s: s["ms"])
+    roofline = {
+        "kernel": dom["kernel"],
+        "bound": dom["bound"],
+        "achieved": dom["achieved"],
+        "peak": dom["peak"],
+        "unit": dom["unit"],
+        "frac": dom["frac"],
+        "traffic": None,
+        "peak_source": peaks["source"] if dom["bound"] == "hbm" else "derived: 148 SM x 64 FP64 FMA/clk x 1.965 GHz (no FP64 figure in MEASURED_PEAKS.json)",
+        "algorithmic": "4*rows*cols bytes per matrix (hbm) / (4/3) n^3 flops per matrix (fp64 tridiagonalisation); DESIGN.md",
+        "hbm_gbs_whole_step": in_bytes / 1e9 / (ms_total / args.steps / 1e3),
+        "hbm_frac_whole_step": in_bytes / 1e9 / (ms_total / args.steps / 1e3) / peaks["hbm_gbs"],
+    }
+
+    # ---------------- CPU baseline on this box (bounded sample, fresh process: no CUDA state is forked)
+    cpu = None
+    if not args.no_cpu_baseline:
+        import subprocess
+
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+        env["CUDA_VISIBLE_DEVICES"] = ""
+        try:
+            out = subprocess.run(
+                [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                capture_output=True, text=True, timeout=600, env=env,
+            )
+            cpu = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception as exc:  # the GPU numbers stand on their own; say why the baseline is missing
+            cpu = {"value": None, "unit": "matrices/s", "cores": host_cores(), "kind": "port", "sample": f"failed: {exc!r}"}
+
+    line = {
+        "metric": "weight matrices spectrally analysed/sec (ViT-Tiny Q/K/V/MLP)",
+        "value": value,
+        "unit": "matrices/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {
+            "workload": SCENARIO["name"],
+            "checkpoints_per_gpu": n_ckpt,
+            "matrices_per_gpu_per_step": matrices,
+            "input_bytes_per_gpu_per_step": in_bytes,
+            "l2": "inputs (987 MB per GPU) larger than L2 (126 MB); no flush needed",
+            "parallelism": f"independent checkpoints per rank x{world}; one NCCL gather of 64-byte records per step",
+            "outputs": "singular values (f64) + 64-byte record per matrix",
+        },
+        "e2e": {"value": e2e_value, "unit": "matrices/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": int(d2h_bytes),
+                "steps": e2e_steps, "api": "vision_spectra_b200.sweep.SweepRunner.run_host (pinned host arenas)"},
+        "gpu_launches": launches,
+        "clocks": clocks.summary(),
+        "roofline": roofline,
+        "roofline_stages": stages,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ckpts", type=int, default=SCENARIO["epochs"] * len(SCENARIO["seeds"]), help="checkpoints per GPU per step")
+    ap.add_argument("--chunk", type=int, default=8, help="checkpoints per H2D/compute pipeline chunk (e2e)")
+    ap.add_argument("--ref-ckpts", type=int, default=4, help="checkpoints per step of the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3  # timing rule: W >= 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

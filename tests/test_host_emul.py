@@ -1,0 +1,80 @@
+"""The product's per-matrix device algorithms (tridiag.cuh, bisect_metrics.cuh) compiled
+for the host, where the cooperative context is one thread, against the golden outputs of
+the real reference.  Catches indexing / numerics bugs without a GPU; the CUDA build of the
+same source is what ships (this host build is test infrastructure)."""
+
+import ctypes
+import json
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+from _compare import metric_close, sv_errors
+from _inputs import build_case, golden_case_names
+
+HERE = Path(__file__).parent
+GOLD = HERE / "golden"
+RECORDS = json.loads((GOLD / "metrics_golden.json").read_text())
+SVS = np.load(GOLD / "sv_golden.npz")
+KEYS = ("spectral_entropy", "stable_rank", "alpha_exponent", "pl_alpha_hill")
+SKIP_SV_ELEM = {"rank1:10", "illcond:50", "powerlaw:100:4.0:f64", "powerlaw:100:2.0:f64"}
+
+
+@pytest.fixture(scope="module")
+def emul():
+    out = HERE / "emul" / "_host_emul.so"
+    src = HERE / "emul" / "host_emul.cpp"
+    deps = [src] + list((HERE.parent / "vision-spectra_b200" / "csrc").glob("*.cuh"))
+    if not out.exists() or any(d.stat().st_mtime > out.stat().st_mtime for d in deps):
+        subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-o", str(out), str(src)], check=True)
+    return ctypes.CDLL(str(out))
+
+
+def run(emul, w, full=0, split=1, fs=-1, fe=-1, hk=-1):
+    w = np.asarray(w, np.float64)
+    g = np.ascontiguousarray(w @ w.T if w.shape[0] <= w.shape[1] else w.T @ w)
+    n = g.shape[0]
+    sv, met, ints = np.zeros(n), np.zeros(4), np.zeros(6, np.int32)
+    emul.vsp_emul_eig_metrics(
+        g.ctypes.data_as(ctypes.c_void_p), n, full, split, fs, fe, hk,
+        sv.ctypes.data_as(ctypes.c_void_p), met.ctypes.data_as(ctypes.c_void_p), ints.ctypes.data_as(ctypes.c_void_p),
+    )
+    return sv, met, ints
+
+
+CASES = [n for n in golden_case_names() if RECORDS[n]["sv_len"] >= 0 or RECORDS[n]["shape"].__len__() == 2]
+CASES = [n for n in CASES if len(RECORDS[n]["shape"]) == 2 and min(RECORDS[n]["shape"]) <= 200]
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("layout", ["packed_split2", "full"])
+def test_emulated_device_algorithm(emul, name, layout):
+    w = build_case(name)
+    g = RECORDS[name]
+    full, split = (1, 1) if layout == "full" else (0, 2)
+    sv, met, ints = run(emul, w, full=full, split=split)
+    for q, k in enumerate(KEYS):
+        if name == "rank1:10" and k in ("alpha_exponent", "pl_alpha_hill"):
+            continue  # functions of LAPACK rounding noise
+        assert metric_close(float(met[q]), g["metrics"][k]), (k, met[q], g["metrics"][k])
+    assert ints[:4].tolist() == [g["ints"]["m"], g["ints"]["start"], g["ints"]["end"], g["ints"]["k"]]
+    if name in SVS.files:
+        nrm, elem = sv_errors(sv, SVS[name])
+        assert nrm < 1e-8
+        if name not in SKIP_SV_ELEM:
+            assert elem < 1e-8, elem
+    else:
+        assert np.all(np.isnan(sv))  # NaN / Inf input
+
+
+def test_emulated_optional_arguments(emul):
+    name = "vit:A:0:q"
+    g = RECORDS[name]
+    w = build_case(name)
+    _, met, ints = run(emul, w, fs=2, fe=12)
+    assert metric_close(float(met[2]), g["alpha_fit_range_2_12"]) and ints[1:3].tolist() == [2, 12]
+    _, met, ints = run(emul, w, hk=7)
+    assert metric_close(float(met[3]), g["hill_k7"]) and ints[3] == 7
+    _, met, _ = run(emul, w, fs=5, fe=4000)
+    assert np.isnan(met[2])

@@ -1,0 +1,135 @@
+// common.cuh -- shared definitions for the weight-spectrum kernels.
+//
+// The per-matrix algorithms (tridiagonalisation, bisection, metrics) are written
+// against a small "cooperative context" (tid / nthreads / sync / all-reduce).  On
+// the device the context is one CTA; compiled by a host compiler it degenerates to
+// a single thread, which lets tests/test_host_emul.py run the very same source on
+// the CPU to check indexing and numerics before any GPU time is spent.  The host
+// build is test infrastructure only; nothing in the product calls it.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+
+#include "../../include/vspectra.h"
+
+#if defined(__CUDACC__)
+#define VSP_DEV __device__ __forceinline__
+#define VSP_HD __host__ __device__ __forceinline__
+#else
+#define VSP_DEV inline
+#define VSP_HD inline
+#endif
+
+namespace vsp {
+
+// One matrix of a batch, as the kernels see it.  Built on the host by the plan,
+// uploaded once; only `ptr` changes between executions.
+struct ItemDesc {
+    const void* ptr;   // device pointer to the row-major matrix
+    int64_t ld;        // row stride in elements
+    int64_t gram_off;  // offset (doubles) of this item's Gram matrix in the workspace
+    int64_t de_off;    // offset (doubles) of d[n], e[n], misc[4]
+    int64_t sv_off;    // offset (doubles) into the packed SV output
+    int32_t rows, cols;
+    int32_t n;         // min(rows, cols): order of the Gram matrix
+    int32_t kdim;      // max(rows, cols): contraction length
+    int32_t trans;     // 1: Gram = W^T W (rows > cols), 0: Gram = W W^T
+    int32_t item;      // index in the caller's batch
+    int32_t full;      // 1: Gram stored full n*n (global-memory eigensolve), 0: packed lower
+    int32_t pad;
+};
+
+VSP_HD int64_t tri(int64_t i) { return (i * (i + 1)) >> 1; }
+
+// misc[] slots written by the tridiagonalisation stage
+enum { MISC_SCALE = 0, MISC_FLAGS = 1, MISC_UNUSED0 = 2, MISC_UNUSED1 = 3, MISC_COUNT = 4 };
+
+#if !defined(__CUDACC__)
+// ----------------------------------------------------------------- host emulation
+using std::copysign;
+using std::fabs;
+using std::fmax;
+using std::fmin;
+using std::frexp;
+using std::isfinite;
+using std::ldexp;
+using std::log;
+using std::sqrt;
+
+struct HostCtx {
+    int tid = 0;
+    int nthreads = 1;
+    void sync() {}
+    double sum(double v) { return v; }
+    double max(double v) { return v; }
+    double min(double v) { return v; }
+    void sum4(double (&v)[4]) { (void)v; }
+    int sum_i(int v) { return v; }
+    int max_i(int v) { return v; }
+};
+#else
+// --------------------------------------------------------------------- device CTA
+// Block all-reduce with one barrier per call: two scratch rows are used alternately,
+// so row A is not rewritten before every thread has passed the barrier of the
+// following reduce (which used row B) and therefore finished reading A.
+struct CtaCtx {
+    int tid;
+    int nthreads;
+    double* red;  // shared scratch: 2 rows x 32 warps x 4 values
+    int flip;
+
+    __device__ CtaCtx(double* scratch) : tid(threadIdx.x), nthreads(blockDim.x), red(scratch), flip(0) {}
+    static constexpr int kScratchDoubles = 2 * 32 * 4;
+
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+
+    template <class Op>
+    __device__ __forceinline__ double reduce(double v, Op op) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+        double* row = red + flip * 128;
+        flip ^= 1;
+        const int nw = (nthreads + 31) >> 5;
+        if ((tid & 31) == 0) row[tid >> 5] = v;
+        __syncthreads();
+        double r = row[0];
+        for (int w = 1; w < nw; ++w) r = op(r, row[w]);
+        return r;
+    }
+    __device__ __forceinline__ double sum(double v) {
+        return reduce(v, [](double a, double b) { return a + b; });
+    }
+    __device__ __forceinline__ double max(double v) {
+        return reduce(v, [](double a, double b) { return fmax(a, b); });
+    }
+    __device__ __forceinline__ double min(double v) {
+        return reduce(v, [](double a, double b) { return fmin(a, b); });
+    }
+    __device__ __forceinline__ void sum4(double (&v)[4]) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+        }
+        double* row = red + flip * 128;
+        flip ^= 1;
+        const int nw = (nthreads + 31) >> 5;
+        if ((tid & 31) == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) row[(tid >> 5) * 4 + q] = v[q];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            double r = row[q];
+            for (int w = 1; w < nw; ++w) r += row[w * 4 + q];
+            v[q] = r;
+        }
+    }
+    __device__ __forceinline__ int sum_i(int v) { return (int)(sum((double)v) + 0.5); }
+    __device__ __forceinline__ int max_i(int v) { return (int)max((double)v); }
+};
+#endif
+
+}  // namespace vsp

@@ -1,0 +1,417 @@
+// vspectra_api.cu -- C-ABI of the weight-spectrum path (see include/vspectra.h).
+//
+// Host side of the drop-in boundary: validates shapes, buckets the ragged batch by
+// shape class (a ViT has three classes, a six-scenario sweep nine), lays
+// out the device workspace and launches the three stages per class on the caller's
+// stream.  No global device state; the only process-wide datum is the launch counter.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "eig_kernels.cuh"
+#include "gram_f64.cuh"
+
+using namespace vsp;
+
+namespace {
+
+std::atomic<int64_t> g_launches{0};
+thread_local std::string t_cuda_error;
+
+inline bool cuda_ok(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    t_cuda_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+}
+#define VSP_CUDA(call)                                 \
+    do {                                               \
+        if (!cuda_ok((call), #call)) return VSP_E_CUDA; \
+    } while (0)
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+inline int64_t round_up64(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+struct ShapeClass {
+    int n;       // order of the Gram matrix
+    int full;    // 1: eigensolve in global memory
+    int begin;   // first item (sorted order)
+    int count;
+    int npad, split;
+};
+
+int validate(int32_t count, const int32_t* rows, const int32_t* cols, const int64_t* ld) {
+    if (count < 0) return VSP_E_ARG;
+    if (count > 0 && (!rows || !cols)) return VSP_E_ARG;
+    for (int i = 0; i < count; ++i) {
+        if (rows[i] < 1 || cols[i] < 1) return VSP_E_ARG;
+        if (ld && ld[i] < cols[i]) return VSP_E_ARG;
+        if (std::min(rows[i], cols[i]) > VSP_MAX_N) return VSP_E_UNSUPPORTED;
+    }
+    return VSP_OK;
+}
+
+}  // namespace
+
+struct vsp_plan {
+    int count = 0;
+    int dtype = VSP_F32;
+    vsp_opts opts{};
+    std::vector<ItemDesc> items;  // sorted by shape class
+    std::vector<int> order;       // sorted position -> caller index
+    std::vector<ShapeClass> classes;
+    int64_t ws_doubles = 0;
+    int64_t sv_total = 0;
+    ItemDesc* d_items = nullptr;
+    int device = -1;
+};
+
+namespace {
+template <typename TIn>
+int launch_gram(const vsp_plan* p, const ShapeClass& c, double* ws, cudaStream_t st) {
+    if (c.n <= 32) {
+        dim3 grid(c.count, 1);
+        gram_f64_kernel<TIn, 32, 32><<<grid, 256, 0, st>>>(p->d_items, c.begin, ws);
+    } else {
+        const int nt = (c.n + 63) / 64;
+        dim3 grid(c.count, nt * (nt + 1) / 2);
+        gram_f64_kernel<TIn, 64, 16><<<grid, 256, 0, st>>>(p->d_items, c.begin, ws);
+    }
+    g_launches++;
+    return cuda_ok(cudaGetLastError(), "gram_f64_kernel") ? VSP_OK : VSP_E_CUDA;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vsp_version(void) { return VSP_VERSION; }
+
+const char* vsp_error_string(int code) {
+    switch (code) {
+        case VSP_OK: return "ok";
+        case VSP_E_ARG: return "invalid argument";
+        case VSP_E_UNSUPPORTED: return "unsupported shape or dtype";
+        case VSP_E_WORKSPACE: return "workspace too small";
+        case VSP_E_CUDA: return "CUDA runtime error";
+        case VSP_E_ALLOC: return "host allocation failed";
+        default: return "unknown error";
+    }
+}
+
+const char* vsp_last_cuda_error(void) { return t_cuda_error.c_str(); }
+
+int64_t vsp_kernel_launch_count(void) { return g_launches.load(); }
+void vsp_reset_kernel_launch_count(void) { g_launches.store(0); }
+
+int vsp_sv_offsets(int32_t count, const int32_t* rows, const int32_t* cols, int64_t* sv_offsets) {
+    const int rc = validate(count, rows, cols, nullptr);
+    if (rc != VSP_OK) return rc;
+    if (!sv_offsets) return VSP_E_ARG;
+    int64_t off = 0;
+    for (int i = 0; i < count; ++i) {
+        sv_offsets[i] = off;
+        off += std::min(rows[i], cols[i]);
+    }
+    sv_offsets[count] = off;
+    return VSP_OK;
+}
+
+static int64_t item_ws_doubles(int n, int full) {
+    const int64_t gram = full ? (int64_t)n * n : tri(n);
+    return round_up64(gram, 4) + round_up64(2 * (int64_t)n + MISC_COUNT, 4);
+}
+
+int64_t vsp_workspace_bytes(int32_t count, const int32_t* rows, const int32_t* cols) {
+    const int rc = validate(count, rows, cols, nullptr);
+    if (rc != VSP_OK) return rc;
+    int64_t total = 0;
+    for (int i = 0; i < count; ++i) {
+        const int n = std::min(rows[i], cols[i]);
+        total += item_ws_doubles(n, n > kSmemMaxN);
+    }
+    return total * (int64_t)sizeof(double) + 256;
+}
+
+int vsp_plan_create(int32_t count, const int32_t* rows, const int32_t* cols, const int64_t* ld, int32_t dtype,
+                    const vsp_opts* opts, vsp_plan** out_plan) {
+    if (!out_plan) return VSP_E_ARG;
+    *out_plan = nullptr;
+    if (dtype != VSP_F32 && dtype != VSP_F64) return VSP_E_UNSUPPORTED;
+    const int rc = validate(count, rows, cols, ld);
+    if (rc != VSP_OK) return rc;
+    vsp_plan* p = new (std::nothrow) vsp_plan();
+    if (!p) return VSP_E_ALLOC;
+    p->count = count;
+    p->dtype = dtype;
+    if (opts) {
+        p->opts = *opts;
+    } else {
+        p->opts.fit_start = p->opts.fit_end = p->opts.hill_k = -1;
+        p->opts.want_sv = -1;
+        p->opts.refine = -1;
+    }
+    // caller-order SV offsets
+    std::vector<int64_t> sv_off(count + 1, 0);
+    for (int i = 0; i < count; ++i) sv_off[i + 1] = sv_off[i] + std::min(rows[i], cols[i]);
+    p->sv_total = sv_off[count];
+    // bucket by Gram order
+    p->order.resize(count);
+    for (int i = 0; i < count; ++i) p->order[i] = i;
+    std::stable_sort(p->order.begin(), p->order.end(), [&](int a, int b) {
+        return std::min(rows[a], cols[a]) < std::min(rows[b], cols[b]);
+    });
+    p->items.resize(count);
+    int64_t off = 0;
+    for (int s = 0; s < count; ++s) {
+        const int i = p->order[s];
+        ItemDesc& it = p->items[s];
+        std::memset(&it, 0, sizeof(it));
+        it.rows = rows[i];
+        it.cols = cols[i];
+        it.ld = ld ? ld[i] : cols[i];
+        it.n = std::min(rows[i], cols[i]);
+        it.kdim = std::max(rows[i], cols[i]);
+        it.trans = rows[i] > cols[i] ? 1 : 0;
+        it.item = i;
+        it.full = it.n > kSmemMaxN ? 1 : 0;
+        it.sv_off = sv_off[i];
+        const int64_t gram = it.full ? (int64_t)it.n * it.n : tri(it.n);
+        it.gram_off = off;
+        off += round_up64(gram, 4);
+        it.de_off = off;
+        off += round_up64(2 * (int64_t)it.n + MISC_COUNT, 4);
+        if (p->classes.empty() || p->classes.back().n != it.n) {
+            ShapeClass c{};
+            c.n = it.n;
+            c.full = it.full;
+            c.begin = s;
+            c.count = 0;
+            c.npad = round_up(it.n, 32);
+            c.split = c.full ? 1 : std::max(1, std::min(4, 384 / c.npad));
+            p->classes.push_back(c);
+        }
+        p->classes.back().count++;
+    }
+    p->ws_doubles = off;
+    if (count > 0) {
+        if (!cuda_ok(cudaGetDevice(&p->device), "cudaGetDevice") ||
+            !cuda_ok(cudaMalloc(&p->d_items, sizeof(ItemDesc) * (size_t)count), "cudaMalloc(items)")) {
+            delete p;
+            return VSP_E_CUDA;
+        }
+    }
+    *out_plan = p;
+    return VSP_OK;
+}
+
+int64_t vsp_plan_workspace_bytes(const vsp_plan* plan) {
+    return plan ? plan->ws_doubles * (int64_t)sizeof(double) + 256 : VSP_E_ARG;
+}
+int64_t vsp_plan_sv_count(const vsp_plan* plan) { return plan ? plan->sv_total : VSP_E_ARG; }
+
+void vsp_plan_destroy(vsp_plan* plan) {
+    if (!plan) return;
+    if (plan->d_items) cudaFree(plan->d_items);
+    delete plan;
+}
+
+static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vsp_record* d_records,
+                        void* d_workspace, int64_t workspace_bytes, void* stream, std::vector<cudaEvent_t>* evs) {
+    if (!p) return VSP_E_ARG;
+    if (p->count == 0) return VSP_OK;
+    if (!d_ptrs || !d_records || !d_workspace) return VSP_E_ARG;
+    if (p->opts.want_sv != 0 && !d_sv) return VSP_E_ARG;
+    // align the workspace to 256 bytes inside the caller's buffer
+    uintptr_t base = reinterpret_cast<uintptr_t>(d_workspace);
+    uintptr_t aligned = (base + 255) & ~uintptr_t(255);
+    if ((int64_t)(aligned - base) + p->ws_doubles * (int64_t)sizeof(double) > workspace_bytes) return VSP_E_WORKSPACE;
+    double* ws = reinterpret_cast<double*>(aligned);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+    for (int s = 0; s < p->count; ++s) {
+        const void* ptr = d_ptrs[p->order[s]];
+        if (!ptr) return VSP_E_ARG;
+        p->items[s].ptr = ptr;
+    }
+    VSP_CUDA(cudaMemcpyAsync(p->d_items, p->items.data(), sizeof(ItemDesc) * (size_t)p->count,
+                             cudaMemcpyHostToDevice, st));
+
+    // per-device attribute; cheap enough to set on every call (one process may drive several GPUs)
+    VSP_CUDA(cudaFuncSetAttribute(tridiag_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VSP_CUDA(cudaFuncSetAttribute(tridiag_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VSP_CUDA(cudaFuncSetAttribute(bisect_metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+
+    auto mark = [&]() -> int {
+        if (!evs) return VSP_OK;
+        cudaEvent_t ev;
+        if (!cuda_ok(cudaEventCreate(&ev), "cudaEventCreate")) return VSP_E_CUDA;
+        evs->push_back(ev);
+        return cuda_ok(cudaEventRecord(ev, st), "cudaEventRecord") ? VSP_OK : VSP_E_CUDA;
+    };
+    for (const ShapeClass& c : p->classes) {
+        int rc = mark();
+        if (rc != VSP_OK) return rc;
+        rc = (p->dtype == VSP_F32) ? launch_gram<float>(p, c, ws, st) : launch_gram<double>(p, c, ws, st);
+        if (rc != VSP_OK) return rc;
+        if ((rc = mark()) != VSP_OK) return rc;
+        if (!c.full) {
+            const int threads = c.split * c.npad;
+            tridiag_smem_kernel<<<c.count, threads, tridiag_smem_bytes(c.n, c.npad, c.split), st>>>(
+                p->d_items, c.begin, ws, c.npad, c.split);
+        } else {
+            const int threads = std::min(1024, c.npad);
+            tridiag_global_kernel<<<c.count, threads, tridiag_global_smem_bytes(c.npad), st>>>(p->d_items, c.begin,
+                                                                                              ws, c.npad);
+        }
+        g_launches++;
+        VSP_CUDA(cudaGetLastError());
+        if ((rc = mark()) != VSP_OK) return rc;
+        const int bthreads = std::min(1024, c.npad);
+        bisect_metrics_kernel<<<c.count, bthreads, bisect_smem_bytes(c.npad), st>>>(p->d_items, c.begin, ws, c.npad,
+                                                                                    p->opts, d_sv, d_records);
+        g_launches++;
+        VSP_CUDA(cudaGetLastError());
+        if ((rc = mark()) != VSP_OK) return rc;
+    }
+    return VSP_OK;
+}
+
+int vsp_plan_execute(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vsp_record* d_records,
+                     void* d_workspace, int64_t workspace_bytes, void* stream) {
+    return execute_impl(p, d_ptrs, d_sv, d_records, d_workspace, workspace_bytes, stream, nullptr);
+}
+
+int vsp_plan_execute_profiled(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vsp_record* d_records,
+                              void* d_workspace, int64_t workspace_bytes, void* stream, float* stage_ms) {
+    if (!stage_ms) return VSP_E_ARG;
+    std::vector<cudaEvent_t> evs;
+    int rc = execute_impl(p, d_ptrs, d_sv, d_records, d_workspace, workspace_bytes, stream, &evs);
+    stage_ms[0] = stage_ms[1] = stage_ms[2] = 0.f;
+    if (rc == VSP_OK && !cuda_ok(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)), "cudaStreamSynchronize"))
+        rc = VSP_E_CUDA;
+    if (rc == VSP_OK) {
+        for (size_t i = 0; i + 3 < evs.size(); i += 4)  // 4 marks per shape class
+            for (int sidx = 0; sidx < 3; ++sidx) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, evs[i + sidx], evs[i + sidx + 1]) == cudaSuccess) stage_ms[sidx] += ms;
+            }
+    }
+    for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
+    return rc;
+}
+
+int vsp_analyze_batch(const void* const* d_ptrs, const int32_t* rows, const int32_t* cols, const int64_t* ld,
+                      int32_t dtype, int32_t count, const vsp_opts* opts, double* d_sv, vsp_record* d_records,
+                      void* d_workspace, int64_t workspace_bytes, void* stream) {
+    vsp_plan* plan = nullptr;
+    int rc = vsp_plan_create(count, rows, cols, ld, dtype, opts, &plan);
+    if (rc != VSP_OK) return rc;
+    rc = vsp_plan_execute(plan, d_ptrs, d_sv, d_records, d_workspace, workspace_bytes, stream);
+    // the item table must outlive the kernels that read it
+    if (plan->d_items) cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream));
+    vsp_plan_destroy(plan);
+    return rc;
+}
+
+int vsp_analyze_batch_host(const void* const* h_ptrs, const int32_t* rows, const int32_t* cols, const int64_t* ld,
+                           int32_t dtype, int32_t count, const vsp_opts* opts, double* h_sv, vsp_record* h_records,
+                           int32_t device) {
+    if (dtype != VSP_F32 && dtype != VSP_F64) return VSP_E_UNSUPPORTED;
+    int rc = validate(count, rows, cols, ld);
+    if (rc != VSP_OK) return rc;
+    if (count == 0) return VSP_OK;
+    if (!h_ptrs || !h_records) return VSP_E_ARG;
+    const bool want_sv = !(opts && opts->want_sv == 0);
+    if (want_sv && !h_sv) return VSP_E_ARG;
+    VSP_CUDA(cudaSetDevice(device));
+    const size_t esz = dtype == VSP_F32 ? 4 : 8;
+
+    // dense device layout, 16-byte aligned; contiguous host ranges become one copy
+    std::vector<int64_t> doff(count + 1, 0);
+    for (int i = 0; i < count; ++i)
+        doff[i + 1] = round_up64(doff[i] + (int64_t)rows[i] * cols[i] * (int64_t)esz, 16);
+    char* d_in = nullptr;
+    void* d_ws = nullptr;
+    double* d_sv = nullptr;
+    vsp_record* d_rec = nullptr;
+    vsp_plan* plan = nullptr;
+    cudaStream_t st = nullptr;
+    auto cleanup = [&]() {
+        if (plan) vsp_plan_destroy(plan);
+        if (d_in) cudaFree(d_in);
+        if (d_ws) cudaFree(d_ws);
+        if (d_sv) cudaFree(d_sv);
+        if (d_rec) cudaFree(d_rec);
+        if (st) cudaStreamDestroy(st);
+    };
+#define VSP_CUDA_C(call)                       \
+    do {                                       \
+        if (!cuda_ok((call), #call)) {         \
+            cleanup();                         \
+            return VSP_E_CUDA;                 \
+        }                                      \
+    } while (0)
+    VSP_CUDA_C(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    rc = vsp_plan_create(count, rows, cols, nullptr, dtype, opts, &plan);
+    if (rc != VSP_OK) {
+        cleanup();
+        return rc;
+    }
+    const int64_t ws_bytes = vsp_plan_workspace_bytes(plan);
+    VSP_CUDA_C(cudaMalloc(&d_in, (size_t)doff[count] + 16));
+    VSP_CUDA_C(cudaMalloc(&d_ws, (size_t)ws_bytes));
+    VSP_CUDA_C(cudaMalloc(&d_rec, sizeof(vsp_record) * (size_t)count));
+    if (want_sv) VSP_CUDA_C(cudaMalloc(&d_sv, sizeof(double) * (size_t)std::max<int64_t>(1, plan->sv_total)));
+
+    std::vector<const void*> dptrs(count);
+    int i = 0;
+    while (i < count) {
+        if (!h_ptrs[i]) {
+            cleanup();
+            return VSP_E_ARG;
+        }
+        dptrs[i] = d_in + doff[i];
+        const int64_t hl = ld ? ld[i] : cols[i];
+        if (hl != cols[i]) {  // strided host view
+            VSP_CUDA_C(cudaMemcpy2DAsync(d_in + doff[i], (size_t)cols[i] * esz, h_ptrs[i], (size_t)hl * esz,
+                                         (size_t)cols[i] * esz, (size_t)rows[i], cudaMemcpyHostToDevice, st));
+            ++i;
+            continue;
+        }
+        // merge a run of host-contiguous, device-contiguous matrices
+        int j = i;
+        int64_t bytes = (int64_t)rows[i] * cols[i] * (int64_t)esz;
+        while (j + 1 < count && h_ptrs[j + 1] &&
+               (!ld || ld[j + 1] == cols[j + 1]) &&
+               static_cast<const char*>(h_ptrs[j + 1]) == static_cast<const char*>(h_ptrs[i]) + bytes &&
+               doff[j + 1] == doff[i] + bytes) {
+            ++j;
+            dptrs[j] = d_in + doff[j];
+            bytes += (int64_t)rows[j] * cols[j] * (int64_t)esz;
+        }
+        VSP_CUDA_C(cudaMemcpyAsync(d_in + doff[i], h_ptrs[i], (size_t)bytes, cudaMemcpyHostToDevice, st));
+        i = j + 1;
+    }
+    rc = vsp_plan_execute(plan, dptrs.data(), d_sv, d_rec, d_ws, ws_bytes, st);
+    if (rc != VSP_OK) {
+        cudaStreamSynchronize(st);
+        cleanup();
+        return rc;
+    }
+    VSP_CUDA_C(cudaMemcpyAsync(h_records, d_rec, sizeof(vsp_record) * (size_t)count, cudaMemcpyDeviceToHost, st));
+    if (want_sv && plan->sv_total > 0)
+        VSP_CUDA_C(cudaMemcpyAsync(h_sv, d_sv, sizeof(double) * (size_t)plan->sv_total, cudaMemcpyDeviceToHost, st));
+    VSP_CUDA_C(cudaStreamSynchronize(st));
+    cleanup();
+    return VSP_OK;
+#undef VSP_CUDA_C
+}
+
+}  // extern "C"

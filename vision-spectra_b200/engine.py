@@ -1,0 +1,311 @@
+"""Batched entry point of the B200 spectral path.
+
+`SpectraEngine.analyze(list_of_matrices)` is the one call that replaces the
+reference's per-matrix Python loop (experiments/run_spectral_analysis.py:323-336,
+training/base.py:399-405): every matrix of a checkpoint goes to the GPU in one
+ragged batch and comes back as one 64-byte record (+ singular values).
+
+PyTorch is used for device memory and streams only; all arithmetic happens in
+lib/libvspectra.so (hand-written sm_100a CUDA behind the C-ABI of
+include/vspectra.h).  There is no CPU fallback: without the library or without a
+CUDA device this module raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from collections import OrderedDict
+from typing import Any, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+METRIC_KEYS = ("spectral_entropy", "stable_rank", "alpha_exponent", "pl_alpha_hill")
+_NAN = float("nan")
+
+
+def nan_metrics() -> dict[str, float]:
+    """The reference's failure value: every metric NaN (spectral.py:87-93)."""
+    return dict.fromkeys(METRIC_KEYS, _NAN)
+
+
+class BatchResult:
+    """Records + singular values of one executed batch, still on the device."""
+
+    __slots__ = ("records", "sv", "sv_offsets", "count")
+
+    def __init__(self, records: torch.Tensor, sv: torch.Tensor | None, sv_offsets: np.ndarray, count: int):
+        self.records = records  # uint8 [count*64]
+        self.sv = sv  # float64 [sum n] or None
+        self.sv_offsets = sv_offsets  # int64 [count+1]
+        self.count = count
+
+    def records_host(self) -> np.ndarray:
+        return self.records.cpu().numpy().view(nat.RECORD_DTYPE)
+
+    def sv_host(self) -> np.ndarray | None:
+        return None if self.sv is None else self.sv.cpu().numpy()
+
+
+class SpectraEngine:
+    """Owns the per-device scratch (workspace, result buffers, cached plans)."""
+
+    def __init__(self, device: torch.device | str | int | None = None, max_cached_plans: int = 8):
+        if not torch.cuda.is_available():
+            raise nat.NativeError("no CUDA device: the spectral path has no CPU fallback")
+        self.lib = nat.load()
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
+        if self.device.type != "cuda":
+            raise nat.NativeError(f"SpectraEngine needs a CUDA device, got {self.device}")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self._plans: OrderedDict[tuple, int] = OrderedDict()
+        self._max_plans = max_cached_plans
+        self._ws: torch.Tensor | None = None
+        self._pinned: torch.Tensor | None = None
+        self._pinned_busy: torch.cuda.Event | None = None
+
+    # ------------------------------------------------------------------ plans
+    def _plan(self, rows, cols, ld, dtype: int, opts: nat.VspOpts) -> int:
+        key = (rows.tobytes(), cols.tobytes(), ld.tobytes(), dtype, opts.fit_start, opts.fit_end, opts.hill_k, opts.want_sv, opts.refine)
+        plan = self._plans.get(key)
+        if plan is not None:
+            self._plans.move_to_end(key)
+            return plan
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            nat.check(
+                self.lib.vsp_plan_create(len(rows), nat.p32(rows), nat.p32(cols), nat.p64(ld), dtype, ctypes.byref(opts), ctypes.byref(handle)),
+                "vsp_plan_create",
+            )
+        self._plans[key] = handle.value
+        while len(self._plans) > self._max_plans:
+            _, old = self._plans.popitem(last=False)
+            torch.cuda.synchronize(self.device)  # kernels may still read the old item table
+            self.lib.vsp_plan_destroy(old)
+        return handle.value
+
+    def close(self) -> None:
+        if self._plans:
+            torch.cuda.synchronize(self.device)
+            for plan in self._plans.values():
+                self.lib.vsp_plan_destroy(plan)
+            self._plans.clear()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --------------------------------------------------------------- device path
+    def analyze_device(
+        self,
+        tensors: Sequence[torch.Tensor],
+        fit_range: tuple[int, int] | None = None,
+        hill_k: int | None = None,
+        want_sv: bool = True,
+    ) -> BatchResult:
+        """Launch the three stages for 2-D CUDA tensors of ONE dtype (float32 or
+        float64) with unit column stride.  Asynchronous on the current stream;
+        the returned buffers are valid once that stream reaches this point."""
+        count = len(tensors)
+        if count == 0:
+            return BatchResult(torch.empty(0, dtype=torch.uint8, device=self.device), None, np.zeros(1, np.int64), 0)
+        dt = tensors[0].dtype
+        if dt not in (torch.float32, torch.float64):
+            raise TypeError(f"analyze_device takes float32/float64 tensors, got {dt}")
+        rows = np.empty(count, np.int32)
+        cols = np.empty(count, np.int32)
+        ld = np.empty(count, np.int64)
+        ptrs = np.empty(count, np.uint64)
+        for i, t in enumerate(tensors):
+            if t.dtype != dt or t.ndim != 2 or t.device != self.device or (t.shape[1] > 1 and t.stride(1) != 1):
+                raise ValueError("analyze_device: tensors must be 2-D, same dtype, on the engine device, unit column stride")
+            rows[i], cols[i] = t.shape
+            ld[i] = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+            if ld[i] < cols[i]:
+                raise ValueError("analyze_device: overlapping rows (stride(0) < cols)")
+            ptrs[i] = t.data_ptr()
+        dtype = nat.VSP_F32 if dt == torch.float32 else nat.VSP_F64
+        return self.analyze_raw(ptrs, rows, cols, ld, dtype, fit_range, hill_k, want_sv)
+
+    def analyze_raw(
+        self,
+        ptrs: np.ndarray,
+        rows: np.ndarray,
+        cols: np.ndarray,
+        ld: np.ndarray,
+        dtype: int,
+        fit_range: tuple[int, int] | None = None,
+        hill_k: int | None = None,
+        want_sv: bool = True,
+        plan: int | None = None,
+        stage_ms: list | None = None,
+    ) -> BatchResult:
+        """Table form of analyze_device: `ptrs` is a uint64 array of device addresses,
+        rows/cols int32, ld int64 (elements).  The caller keeps the memory alive until
+        the stream has passed this point.  Passing a `plan` (from `make_plan`) skips the
+        shape-table lookup for repeated batches."""
+        count = int(len(ptrs))
+        ptrs = np.ascontiguousarray(ptrs, dtype=np.uint64)
+        if plan is None:
+            plan = self.make_plan(rows, cols, ld, dtype, fit_range, hill_k, want_sv)
+        ws_bytes = self.lib.vsp_plan_workspace_bytes(plan)
+        sv_count = self.lib.vsp_plan_sv_count(plan)
+        if self._ws is None or self._ws.numel() < ws_bytes:
+            self._ws = None
+            self._ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=self.device)
+        records = torch.empty(count * nat.RECORD_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
+        sv = torch.empty(int(sv_count), dtype=torch.float64, device=self.device) if want_sv else None
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        args = (
+            plan,
+            ptrs.ctypes.data_as(ctypes.POINTER(ctypes.c_void_p)),
+            None if sv is None else sv.data_ptr(),
+            records.data_ptr(),
+            self._ws.data_ptr(),
+            int(self._ws.numel()),
+            stream,
+        )
+        with torch.cuda.device(self.device):
+            if stage_ms is None:
+                nat.check(self.lib.vsp_plan_execute(*args), "vsp_plan_execute")
+            else:  # per-stage CUDA-event timing (synchronises); used by bench.py's roofline
+                ms = (ctypes.c_float * 3)()
+                nat.check(self.lib.vsp_plan_execute_profiled(*args, ms), "vsp_plan_execute_profiled")
+                stage_ms[:] = [float(ms[0]), float(ms[1]), float(ms[2])]
+        offs = np.zeros(count + 1, np.int64)
+        np.cumsum(np.minimum(rows, cols), out=offs[1:])
+        return BatchResult(records, sv, offs, count)
+
+    def make_plan(self, rows, cols, ld, dtype: int, fit_range=None, hill_k=None, want_sv: bool = True) -> int:
+        """Validated, device-resident shape table for a batch (cached per engine)."""
+        opts = nat.VspOpts.make(fit_range, hill_k, want_sv)
+        return self._plan(nat.i32(rows), nat.i32(cols), nat.i64(ld), dtype, opts)
+
+    # ----------------------------------------------------------------- host path
+    def _stage_host(self, arrays: list[np.ndarray], np_dtype) -> list[torch.Tensor]:
+        """Copy host matrices through one pinned arena and one H2D transfer."""
+        sizes = [a.size for a in arrays]
+        total = int(sum(sizes))
+        tdt = torch.float32 if np_dtype == np.float32 else torch.float64
+        nbytes = total * np.dtype(np_dtype).itemsize
+        if self._pinned_busy is not None:  # the previous H2D copy may still be reading the arena
+            self._pinned_busy.synchronize()
+        if self._pinned is None or self._pinned.numel() < nbytes:
+            self._pinned = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8).pin_memory()
+        arena = self._pinned[:nbytes].view(tdt)
+        arena_np = arena.numpy()
+        off = 0
+        for a, sz in zip(arrays, sizes):
+            arena_np[off : off + sz] = np.asarray(a, dtype=np_dtype).reshape(-1)
+            off += sz
+        dev = arena.to(self.device, non_blocking=True)
+        self._pinned_busy = torch.cuda.Event()
+        self._pinned_busy.record(torch.cuda.current_stream(self.device))
+        out, off = [], 0
+        for a, sz in zip(arrays, sizes):
+            out.append(dev[off : off + sz].view(a.shape))
+            off += sz
+        return out
+
+    def analyze(
+        self,
+        matrices: Sequence[Any],
+        fit_range: tuple[int, int] | None = None,
+        hill_k: int | None = None,
+        want_sv: bool = True,
+    ) -> tuple[list[dict[str, float]], list[np.ndarray | None], np.ndarray]:
+        """Analyse a ragged list of matrices (torch tensors on any device or NumPy
+        arrays, any float dtype).  Returns (metrics dicts, singular-value arrays,
+        records) in input order.  Anything the reference would answer with NaN
+        (non-2-D input, empty matrix, NaN/Inf entries) yields NaN metrics and
+        `None` singular values; nothing raises for bad *data*.
+
+        float64 inputs are analysed from their float64 values, everything else is
+        widened/narrowed to float32 first (model weights are fp32/bf16/fp16)."""
+        count = len(matrices)
+        metrics: list[dict[str, float]] = [nan_metrics() for _ in range(count)]
+        svs: list[np.ndarray | None] = [None] * count
+        records = np.zeros(count, nat.RECORD_DTYPE)
+        records["item"] = np.arange(count)
+        records["status"] = nat.ST_NONFINITE
+        records["start"] = records["end"] = records["k"] = -1
+        records["metrics"] = np.nan
+        groups: dict[Any, list[tuple[int, Any]]] = {torch.float32: [], torch.float64: []}
+        host: dict[Any, list[tuple[int, np.ndarray]]] = {np.float32: [], np.float64: []}
+        for i, w in enumerate(matrices):
+            if isinstance(w, torch.Tensor):
+                w = w.detach()
+                if w.ndim != 2 or w.numel() == 0:
+                    continue
+                if w.device.type == "cuda":
+                    if w.device != self.device:
+                        w = w.to(self.device)
+                    if w.dtype not in (torch.float32, torch.float64):
+                        w = w.float()
+                    if (w.shape[1] > 1 and w.stride(1) != 1) or (w.shape[0] > 1 and w.stride(0) < w.shape[1]):
+                        w = w.contiguous()
+                    groups[w.dtype].append((i, w))
+                    continue
+                w = w.float().numpy() if w.dtype not in (torch.float32, torch.float64) else w.numpy()
+            else:
+                w = np.asarray(w)
+                if w.dtype.kind not in "fiub":
+                    continue
+            if w.ndim != 2 or w.size == 0:
+                continue
+            npdt = np.float64 if w.dtype == np.float64 else np.float32
+            host[npdt].append((i, w))
+        for npdt, lst in host.items():
+            if lst:
+                staged = self._stage_host([w for _, w in lst], npdt)
+                tdt = torch.float32 if npdt == np.float32 else torch.float64
+                groups[tdt] += [(i, t) for (i, _), t in zip(lst, staged)]
+        pending = []
+        for tdt, lst in groups.items():
+            if lst:
+                lst.sort(key=lambda p: p[0])
+                res = self.analyze_device([t for _, t in lst], fit_range, hill_k, want_sv)
+                pending.append((lst, res))
+        for lst, res in pending:
+            rec = res.records_host()
+            sv = res.sv_host()
+            for j, (i, _) in enumerate(lst):
+                r = rec[j]
+                records[i] = r
+                records[i]["item"] = i
+                metrics[i] = {k: float(r["metrics"][q]) for q, k in enumerate(METRIC_KEYS)}
+                if sv is not None and not (int(r["status"]) & nat.ST_NONFINITE):
+                    svs[i] = sv[res.sv_offsets[j] : res.sv_offsets[j + 1]].copy()
+        return metrics, svs, records
+
+
+_default_engines: dict[int, SpectraEngine] = {}
+
+
+def default_engine(device: torch.device | None = None) -> SpectraEngine:
+    """One engine per CUDA device of this process."""
+    if not torch.cuda.is_available():
+        raise nat.NativeError("no CUDA device: the spectral path has no CPU fallback")
+    idx = torch.cuda.current_device() if device is None or device.index is None else device.index
+    eng = _default_engines.get(idx)
+    if eng is None:
+        eng = _default_engines[idx] = SpectraEngine(torch.device("cuda", idx))
+    return eng
+
+
+def analyze_matrices(matrices: Sequence[Any], **kw) -> tuple[list[dict[str, float]], list[np.ndarray | None]]:
+    """SURVEY 8b's batched entry: list of matrices -> (list of metric dicts, list of SV arrays)."""
+    device = None
+    for w in matrices:
+        if isinstance(w, torch.Tensor) and w.device.type == "cuda":
+            device = w.device
+            break
+    metrics, svs, _ = default_engine(device).analyze(matrices, **kw)
+    return metrics, svs

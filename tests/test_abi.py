@@ -57,7 +57,7 @@ def test_shape_validation_and_layout_queries(lib):
 
     rows, cols = nat.i32([32, 128, 32, 768]), nat.i32([32, 32, 128, 3072])
     ws = lib.vsp_workspace_bytes(4, nat.p32(rows), nat.p32(cols))
-    expect = sum(((n * (n + 1) // 2 + 3) // 4 * 4 if n <= 224 else n * n) + (2 * n + 4 + 3) // 4 * 4 for n in (32, 32, 32, 768))
+    expect = sum(((n * (n + 1) // 2 + 3) // 4 * 4 if n <= 216 else n * n) + (2 * n + 4 + 3) // 4 * 4 for n in (32, 32, 32, 768))
     assert ws == expect * 8 + 256
     offs = np.zeros(5, np.int64)
     assert lib.vsp_sv_offsets(4, nat.p32(rows), nat.p32(cols), nat.p64(offs)) == 0

@@ -23,44 +23,89 @@ namespace vsp {
 
 struct TriInfo {
     double gl, gu;   // Gershgorin interval, widened
-    double pivmin;   // smallest pivot magnitude allowed in the Sturm recurrence
     double atol;     // absolute width at which bisection stops
 };
 
-// Number of eigenvalues of T (diag d, squared off-diag e2) that are < x  (LAPACK
-// dlaebz convention: a pivot <= 0 counts).
-VSP_DEV int sturm_count(const double* d, const double* e2, int n, double x, double pivmin) {
-    double q = d[0] - x;
-    if (fabs(q) < pivmin) q = -pivmin;
-    int c = (q <= 0.0);
+// sign / zero tests on the bit pattern: integer pipe on the device, so the FP64 pipe
+// only sees the three arithmetic instructions of the recurrence.
+VSP_DEV bool dbl_neg(double x) {
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(x) < 0;
+#else
+    return std::signbit(x);
+#endif
+}
+VSP_DEV bool dbl_zero(double x) {
+#if defined(__CUDA_ARCH__)
+    return ((__double2hiint(x) & 0x7fffffff) | __double2loint(x)) == 0;
+#else
+    return x == 0.0;
+#endif
+}
+// 2^(1023 - biased_exponent(max(|a|,|b|))): multiplying by it brings the pair back to O(1).
+VSP_DEV double rescale_factor(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    int ea = (__double2hiint(a) >> 20) & 0x7ff, eb = (__double2hiint(b) >> 20) & 0x7ff;
+    int ex = ea > eb ? ea : eb;
+    if (ex == 0 || ex == 0x7ff) return 1.0;
+    return __hiloint2double((2046 - ex) << 20, 0);
+#else
+    int ea, eb;
+    (void)frexp(a, &ea);
+    (void)frexp(b, &eb);
+    if (a == 0.0 && b == 0.0) return 1.0;
+    int ex = (a == 0.0) ? eb : (b == 0.0 ? ea : (ea > eb ? ea : eb));
+    return ldexp(1.0, 1 - ex);
+#endif
+}
+
+// Number of eigenvalues of T (diag d, squared off-diagonals e2) below x, as the number
+// of sign changes in the Sturm sequence p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}
+// (division free: three FP64 instructions per row).  A zero p_i takes the sign opposite
+// to p_{i-1}, which is LAPACK dlaebz's "pivot <= 0 counts, |pivot| < pivmin -> -pivmin".
+// The pair is renormalised every 8 rows; T is pre-scaled to ||T|| <= O(n), so |p| cannot
+// overflow or vanish between renormalisations.
+VSP_DEV int sturm_count(const double* d, const double* e2, int n, double x) {
+    double p0 = 1.0;
+    double p1 = d[0] - x;
+    if (dbl_zero(p1)) p1 = -2.4e-181;
+    int c = dbl_neg(p1) ? 1 : 0;
     for (int i = 1; i < n; ++i) {
-        q = d[i] - x - e2[i - 1] / q;
-        if (fabs(q) < pivmin) q = -pivmin;
-        c += (q <= 0.0);
+        const double t = d[i] - x;
+        double p2 = fma(t, p1, -(e2[i - 1] * p0));
+        if (dbl_zero(p2)) p2 = -p1 * 2.4e-181;
+        c += (dbl_neg(p2) != dbl_neg(p1)) ? 1 : 0;
+        p0 = p1;
+        p1 = p2;
+        if ((i & 7) == 7) {
+            const double s = rescale_factor(p0, p1);
+            p0 *= s;
+            p1 *= s;
+        }
     }
     return c;
 }
 
 template <class Ctx>
 VSP_DEV TriInfo tri_bounds(Ctx& ctx, const double* d, const double* e, int n) {
-    double lo = 1e300, hi = -1e300, emax = 0.0;
+    double lo = 1e300, hi = -1e300;
     for (int i = ctx.tid; i < n; i += ctx.nthreads) {
         const double el = (i > 0) ? fabs(e[i - 1]) : 0.0;
         const double er = (i < n - 1) ? fabs(e[i]) : 0.0;
         lo = fmin(lo, d[i] - el - er);
         hi = fmax(hi, d[i] + el + er);
-        emax = fmax(emax, er * er);
     }
     lo = ctx.min(lo);
     hi = ctx.max(hi);
-    emax = ctx.max(emax);
     TriInfo t;
     const double bnorm = fmax(fabs(lo), fabs(hi));
-    t.pivmin = 2.2250738585072014e-308 * fmax(1.0, emax);
-    const double widen = 2.0 * bnorm * 2.220446049250313e-16 * n + 2.0 * t.pivmin;
+    const double widen = 2.0 * bnorm * 2.220446049250313e-16 * n + 4.4501477170144028e-308;
     t.gl = lo - widen;
     t.gu = hi + widen;
-    t.atol = bnorm * 8.470329472543003e-22;  // 2^-70 * ||T||: far below the reduction's own error
+    // Absolute floor of the interval width.  Householder reduction of a graded Gram matrix
+    // keeps small eigenvalues far better than its eps ||T|| worst case (power-law spectra,
+    // tests/test_metrics.py:113-135), so resolve well below eps ||T||: 2^-66 ||T||.
+    t.atol = bnorm * 1.3552527156068805e-20;
     return t;
 }
 
@@ -76,7 +121,7 @@ VSP_DEV int bisect_all(Ctx& ctx, const double* d, const double* e2, int n, const
             const double mid = 0.5 * (lo + hi);
             const double tol = fmax(t.atol, 4.440892098500626e-16 * fmax(fabs(lo), fabs(hi)));
             if (hi - lo <= tol || mid <= lo || mid >= hi) break;
-            if (sturm_count(d, e2, n, mid, t.pivmin) >= k + 1)
+            if (sturm_count(d, e2, n, mid) >= k + 1)
                 hi = mid;
             else
                 lo = mid;

@@ -1,7 +1,7 @@
 // eig_kernels.cuh -- CTA wrappers around tridiag.cuh / bisect_metrics.cuh.
 //
-//   tridiag_smem_kernel   n <= kSmemMaxN : Gram (packed lower) copied into shared
-//                         memory once, reduced there, only d/e (2n doubles) go back.
+//   tridiag_fused_kernel  n <= kSmemMaxN : (tridiag_fused.cuh) Gram (packed lower) copied
+//                         into shared memory once, reduced there, only d/e go back.
 //   tridiag_global_kernel larger n       : Gram (full, symmetric) reduced in place in
 //                         global memory / L2 with coalesced column walks.
 //   bisect_metrics_kernel all n          : d/e -> sorted eigenvalues -> singular values,
@@ -10,66 +10,17 @@
 
 #include "bisect_metrics.cuh"
 #include "tridiag.cuh"
+#include "tridiag_fused.cuh"
 
 namespace vsp {
 
-constexpr int kSmemMaxN = 224;  // tri(224)*8 + vectors < 227 KB
+constexpr int kSmemMaxN = 216;  // tri(216)*8 + (6+14)*224*8 + scratch < 227 KB
 
-__host__ __device__ inline size_t tridiag_smem_bytes(int n, int npad, int split) {
-    return sizeof(double) * ((size_t)tri(n) + 4 * (size_t)npad + (size_t)split * npad + CtaCtx::kScratchDoubles);
-}
 __host__ __device__ inline size_t tridiag_global_smem_bytes(int npad) {
     return sizeof(double) * (5 * (size_t)npad + CtaCtx::kScratchDoubles);
 }
 __host__ __device__ inline size_t bisect_smem_bytes(int npad) {
     return sizeof(double) * (3 * (size_t)npad + CtaCtx::kScratchDoubles);
-}
-
-__global__ void tridiag_smem_kernel(const ItemDesc* __restrict__ items, int item_base, double* __restrict__ ws,
-                                    int npad, int split) {
-    extern __shared__ __align__(16) double smem[];
-    const ItemDesc it = items[item_base + blockIdx.x];
-    const int n = it.n;
-    double* red = smem;
-    double* v = red + CtaCtx::kScratchDoubles;
-    double* p = v + npad;
-    double* d = p + npad;
-    double* e = d + npad;
-    double* part = e + npad;
-    double* a = part + (size_t)split * npad;
-    CtaCtx ctx(red);
-
-    const double* __restrict__ G = ws + it.gram_off;
-    double md = 0.0;
-    int bad = 0;
-    for (int i = ctx.tid; i < n; i += ctx.nthreads) {
-        const double g = G[tri(i) + i];
-        if (!isfinite(g)) bad = 1;
-        md = fmax(md, g);
-    }
-    int flags = 0;
-    const double scale = gram_scale(ctx, md, bad, &flags);
-    double* out = ws + it.de_off;
-    if (flags) {  // nothing to reduce: bisect stage only needs the flags
-        for (int i = ctx.tid; i < 2 * n; i += ctx.nthreads) out[i] = 0.0;
-        if (ctx.tid == 0) {
-            out[2 * n + MISC_SCALE] = 1.0;
-            out[2 * n + MISC_FLAGS] = (double)flags;
-        }
-        return;
-    }
-    const int total = (int)tri(n);
-    for (int i = ctx.tid; i < total; i += ctx.nthreads) a[i] = G[i] * scale;
-    ctx.sync();
-    tridiagonalize(ctx, PackedLower{a, n}, n, npad, split, d, e, v, p, part);
-    for (int i = ctx.tid; i < n; i += ctx.nthreads) {
-        out[i] = d[i];
-        out[n + i] = e[i];
-    }
-    if (ctx.tid == 0) {
-        out[2 * n + MISC_SCALE] = scale;
-        out[2 * n + MISC_FLAGS] = 0.0;
-    }
 }
 
 __global__ void tridiag_global_kernel(const ItemDesc* __restrict__ items, int item_base, double* __restrict__ ws,

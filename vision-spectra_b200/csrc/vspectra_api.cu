@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -244,7 +245,6 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
                              cudaMemcpyHostToDevice, st));
 
     // per-device attribute; cheap enough to set on every call (one process may drive several GPUs)
-    VSP_CUDA(cudaFuncSetAttribute(tridiag_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VSP_CUDA(cudaFuncSetAttribute(tridiag_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VSP_CUDA(cudaFuncSetAttribute(bisect_metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 
@@ -262,9 +262,34 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
         if (rc != VSP_OK) return rc;
         if ((rc = mark()) != VSP_OK) return rc;
         if (!c.full) {
-            const int threads = c.split * c.npad;
-            tridiag_smem_kernel<<<c.count, threads, tridiag_smem_bytes(c.n, c.npad, c.split), st>>>(
-                p->d_items, c.begin, ws, c.npad, c.split);
+            static const int rows_per_warp = [] {  // tuning knob (experiments only)
+                const char* e = std::getenv("VSP_FUSED_ROWS_PER_WARP");
+                const int v = e ? std::atoi(e) : 0;
+                return v > 0 ? v : 24;
+            }();
+            const int nw = fused_warps(c.n, rows_per_warp);
+            const int rows_smem = fused_rows_in_smem(c.n, c.npad, nw);
+            const size_t smem = tridiag_fused_smem_bytes(rows_smem, c.npad, nw);
+            switch ((c.n + 31) / 32) {
+#define VSP_FUSED_CASE(NQ)                                                                                    \
+    case NQ:                                                                                                  \
+        VSP_CUDA(cudaFuncSetAttribute(tridiag_fused_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                      (int)kFusedSmemBudget));                                                \
+        VSP_CUDA(cudaFuncSetAttribute(tridiag_fused_kernel<NQ>, cudaFuncAttributePreferredSharedMemoryCarveout, \
+                                      cudaSharedmemCarveoutMaxShared));                                       \
+        tridiag_fused_kernel<NQ><<<c.count, 32 * nw, smem, st>>>(p->d_items, c.begin, ws, c.npad, rows_smem); \
+        break;
+                VSP_FUSED_CASE(1)
+                VSP_FUSED_CASE(2)
+                VSP_FUSED_CASE(3)
+                VSP_FUSED_CASE(4)
+                VSP_FUSED_CASE(5)
+                VSP_FUSED_CASE(6)
+                VSP_FUSED_CASE(7)
+#undef VSP_FUSED_CASE
+                default:
+                    return VSP_E_UNSUPPORTED;
+            }
         } else {
             const int threads = std::min(1024, c.npad);
             tridiag_global_kernel<<<c.count, threads, tridiag_global_smem_bytes(c.npad), st>>>(p->d_items, c.begin,

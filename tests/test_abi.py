@@ -57,15 +57,15 @@ def test_shape_validation_and_layout_queries(lib):
 
     rows, cols = nat.i32([32, 128, 32, 768]), nat.i32([32, 32, 128, 3072])
     ws = lib.vsp_workspace_bytes(4, nat.p32(rows), nat.p32(cols))
-    expect = sum(((n * (n + 1) // 2 + 3) // 4 * 4 if n <= 216 else n * n) + (2 * n + 4 + 3) // 4 * 4 for n in (32, 32, 32, 768))
-    assert ws == expect * 8 + 256
+    expect = sum(((n * (n + 1) // 2 + (n + 1) // 2 + 3) // 4 * 4 if n <= 256 else n * n) + (2 * n + 4 + 3) // 4 * 4 for n in (32, 32, 32, 768))
+    assert ws == expect * 8 + 1024
     offs = np.zeros(5, np.int64)
     assert lib.vsp_sv_offsets(4, nat.p32(rows), nat.p32(cols), nat.p64(offs)) == 0
     assert offs.tolist() == [0, 32, 64, 96, 864]
     assert lib.vsp_workspace_bytes(-1, nat.p32(rows), nat.p32(cols)) == -1
     assert lib.vsp_workspace_bytes(4, nat.p32(nat.i32([0, 1, 1, 1])), nat.p32(cols)) == -1
     assert lib.vsp_workspace_bytes(1, nat.p32(nat.i32([5000])), nat.p32(nat.i32([6000]))) == -2
-    assert lib.vsp_workspace_bytes(0, None, None) == 256
+    assert lib.vsp_workspace_bytes(0, None, None) == 1024
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -53,7 +53,8 @@ def build_native(force: bool = False, verbose: bool = False) -> Path:
     if not force and not is_stale():
         return LIB
     LIB.parent.mkdir(parents=True, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB), *[str(s) for s in sources()]]
+    extra = os.environ.get("VSP_EXTRA_NVCC_FLAGS", "").split()  # development switches, e.g. -DVSP_PHASE_TIMING
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-o", str(LIB), *[str(s) for s in sources()]]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -14,7 +14,7 @@
 
 namespace vsp {
 
-constexpr int kSmemMaxN = 216;  // tri(216)*8 + (6+14)*224*8 + scratch < 227 KB
+constexpr int kSmemMaxN = 256;  // fused path: 4 chunk pairs of 64 columns; rows beyond 113 KB stay in L2
 
 __host__ __device__ inline size_t tridiag_global_smem_bytes(int npad) {
     return sizeof(double) * (5 * (size_t)npad + CtaCtx::kScratchDoubles);

@@ -125,7 +125,7 @@ int vsp_sv_offsets(int32_t count, const int32_t* rows, const int32_t* cols, int6
 }
 
 static int64_t item_ws_doubles(int n, int full) {
-    const int64_t gram = full ? (int64_t)n * n : tri(n);
+    const int64_t gram = full ? (int64_t)n * n : poff(n);
     return round_up64(gram, 4) + round_up64(2 * (int64_t)n + MISC_COUNT, 4);
 }
 
@@ -137,7 +137,7 @@ int64_t vsp_workspace_bytes(int32_t count, const int32_t* rows, const int32_t* c
         const int n = std::min(rows[i], cols[i]);
         total += item_ws_doubles(n, n > kSmemMaxN);
     }
-    return total * (int64_t)sizeof(double) + 256;
+    return total * (int64_t)sizeof(double) + 1024;
 }
 
 int vsp_plan_create(int32_t count, const int32_t* rows, const int32_t* cols, const int64_t* ld, int32_t dtype,
@@ -183,7 +183,7 @@ int vsp_plan_create(int32_t count, const int32_t* rows, const int32_t* cols, con
         it.item = i;
         it.full = it.n > kSmemMaxN ? 1 : 0;
         it.sv_off = sv_off[i];
-        const int64_t gram = it.full ? (int64_t)it.n * it.n : tri(it.n);
+        const int64_t gram = it.full ? (int64_t)it.n * it.n : poff(it.n);
         it.gram_off = off;
         off += round_up64(gram, 4);
         it.de_off = off;
@@ -213,7 +213,7 @@ int vsp_plan_create(int32_t count, const int32_t* rows, const int32_t* cols, con
 }
 
 int64_t vsp_plan_workspace_bytes(const vsp_plan* plan) {
-    return plan ? plan->ws_doubles * (int64_t)sizeof(double) + 256 : VSP_E_ARG;
+    return plan ? plan->ws_doubles * (int64_t)sizeof(double) + 1024 : VSP_E_ARG;
 }
 int64_t vsp_plan_sv_count(const vsp_plan* plan) { return plan ? plan->sv_total : VSP_E_ARG; }
 
@@ -267,25 +267,25 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
                 const int v = e ? std::atoi(e) : 0;
                 return v > 0 ? v : 24;
             }();
+            static const int debug_timing = std::getenv("VSP_DEBUG_TIMING") ? 1 : 0;
             const int nw = fused_warps(c.n, rows_per_warp);
-            const int rows_smem = fused_rows_in_smem(c.n, c.npad, nw);
-            const size_t smem = tridiag_fused_smem_bytes(rows_smem, c.npad, nw);
-            switch ((c.n + 31) / 32) {
+            const int npad64 = round_up(c.n, 64);  // lanes address column pairs up to 64*NP - 1
+            const int rows_smem = fused_rows_in_smem(c.n, npad64, nw);
+            const size_t smem = tridiag_fused_smem_bytes(rows_smem, npad64, nw);
+            switch ((c.n + 63) / 64) {
 #define VSP_FUSED_CASE(NQ)                                                                                    \
     case NQ:                                                                                                  \
         VSP_CUDA(cudaFuncSetAttribute(tridiag_fused_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                       (int)kFusedSmemBudget));                                                \
         VSP_CUDA(cudaFuncSetAttribute(tridiag_fused_kernel<NQ>, cudaFuncAttributePreferredSharedMemoryCarveout, \
                                       cudaSharedmemCarveoutMaxShared));                                       \
-        tridiag_fused_kernel<NQ><<<c.count, 32 * nw, smem, st>>>(p->d_items, c.begin, ws, c.npad, rows_smem); \
+        tridiag_fused_kernel<NQ><<<c.count, 32 * nw, smem, st>>>(p->d_items, c.begin, ws, npad64, rows_smem,  \
+                                                                  debug_timing);                               \
         break;
                 VSP_FUSED_CASE(1)
                 VSP_FUSED_CASE(2)
                 VSP_FUSED_CASE(3)
                 VSP_FUSED_CASE(4)
-                VSP_FUSED_CASE(5)
-                VSP_FUSED_CASE(6)
-                VSP_FUSED_CASE(7)
 #undef VSP_FUSED_CASE
                 default:
                     return VSP_E_UNSUPPORTED;

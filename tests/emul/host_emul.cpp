@@ -39,8 +39,12 @@ extern "C" int vsp_emul_eig_metrics(const double* gram, int n, int use_full, int
     else
         tridiagonalize(ctx, PackedLower{a.data(), n}, n, npad, split, d.data(), e.data(), v.data(), p.data(), part.data());
     TriInfo t = tri_bounds(ctx, d.data(), e.data(), n);
-    for (int i = 0; i < n; ++i) e[i] = e[i] * e[i];
-    const int iters = bisect_all(ctx, d.data(), e.data(), n, t, lam.data());
+    std::vector<DE> de(n);
+    for (int i = 0; i < n; ++i) {
+        de[i].d = d[i];
+        de[i].e2 = i > 0 ? std::fmax(e[i - 1] * e[i - 1], kE2Floor) : 0.0;
+    }
+    const int iters = bisect_all(ctx, de.data(), n, t, lam.data());
     MetricOut out = spectral_metrics(ctx, lam.data(), n, scale, flags, fit_start, fit_end, hill_k, sv);
     for (int q = 0; q < 4; ++q) metrics4[q] = out.metrics[q];
     ints6[0] = out.m;

@@ -26,22 +26,6 @@ struct TriInfo {
     double atol;     // absolute width at which bisection stops
 };
 
-// sign / zero tests on the bit pattern: integer pipe on the device, so the FP64 pipe
-// only sees the three arithmetic instructions of the recurrence.
-VSP_DEV bool dbl_neg(double x) {
-#if defined(__CUDA_ARCH__)
-    return __double2hiint(x) < 0;
-#else
-    return std::signbit(x);
-#endif
-}
-VSP_DEV bool dbl_zero(double x) {
-#if defined(__CUDA_ARCH__)
-    return ((__double2hiint(x) & 0x7fffffff) | __double2loint(x)) == 0;
-#else
-    return x == 0.0;
-#endif
-}
 // 2^(1023 - biased_exponent(max(|a|,|b|))): multiplying by it brings the pair back to O(1).
 VSP_DEV double rescale_factor(double a, double b) {
 #if defined(__CUDA_ARCH__)
@@ -59,31 +43,83 @@ VSP_DEV double rescale_factor(double a, double b) {
 #endif
 }
 
-// Number of eigenvalues of T (diag d, squared off-diagonals e2) below x, as the number
-// of sign changes in the Sturm sequence p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}
-// (division free: three FP64 instructions per row).  A zero p_i takes the sign opposite
-// to p_{i-1}, which is LAPACK dlaebz's "pivot <= 0 counts, |pivot| < pivmin -> -pivmin".
-// The pair is renormalised every 8 rows; T is pre-scaled to ||T|| <= O(n), so |p| cannot
-// overflow or vanish between renormalisations.
-VSP_DEV int sturm_count(const double* d, const double* e2, int n, double x) {
-    double p0 = 1.0;
-    double p1 = d[0] - x;
-    if (dbl_zero(p1)) p1 = -2.4e-181;
-    int c = dbl_neg(p1) ? 1 : 0;
-    for (int i = 1; i < n; ++i) {
-        const double t = d[i] - x;
-        double p2 = fma(t, p1, -(e2[i - 1] * p0));
-        if (dbl_zero(p2)) p2 = -p1 * 2.4e-181;
-        c += (dbl_neg(p2) != dbl_neg(p1)) ? 1 : 0;
-        p0 = p1;
-        p1 = p2;
-        if ((i & 7) == 7) {
-            const double s = rescale_factor(p0, p1);
-            p0 *= s;
-            p1 *= s;
+// Sign-change bookkeeping on the integer pipe: the high words of consecutive Sturm terms
+// are XORed and the resulting sign bit is funnel-shifted into a 32-bit history that is
+// pop-counted every 32 rows.  The FP64 pipe only sees the three arithmetic instructions.
+struct SignCounter {
+    unsigned hist = 0;
+    int count = 0;
+    VSP_DEV void push(double prev, double cur) {
+#if defined(__CUDA_ARCH__)
+        hist = __funnelshift_l((unsigned)(__double2hiint(prev) ^ __double2hiint(cur)), hist, 1);
+#else
+        hist = (hist << 1) | (std::signbit(prev) != std::signbit(cur) ? 1u : 0u);
+#endif
+    }
+    VSP_DEV void flush() {
+#if defined(__CUDA_ARCH__)
+        count += __popc(hist);
+#else
+        count += __builtin_popcount(hist);
+#endif
+        hist = 0;
+    }
+};
+
+// Number of eigenvalues of T below xa and below xb (two shifts per work item share the
+// loads and give the FP64 pipe two independent chains).  de[i] = (d_i, e2_{i-1}) with
+// e2 = max(e^2, kE2Floor) and e2_{-1} = 0.  Sturm sequence in product form,
+//     p_i = (d_i - x) p_{i-1} - e2_{i-1} p_{i-2},
+// three FP64 instructions per row and shift; the count is the number of sign changes.
+// Because e2 > 0, a term that is exactly zero is followed by one of the sign opposite to its
+// predecessor, which is LAPACK dlaebz's convention (a zero pivot counts as negative), so no
+// zero test is needed.  The pairs are renormalised every 8 rows; T is pre-scaled to
+// ||T|| <= O(n), so |p| can neither overflow nor vanish in between.
+constexpr double kE2Floor = 1e-200;
+
+struct DE {
+    double d, e2;
+};
+
+VSP_DEV void sturm_step(const DE r, double xa, double xb, double& a0, double& a1, double& b0, double& b1,
+                        SignCounter& ca, SignCounter& cb) {
+    const double a2 = fma(r.d - xa, a1, -(r.e2 * a0));
+    const double b2 = fma(r.d - xb, b1, -(r.e2 * b0));
+    ca.push(a1, a2);
+    cb.push(b1, b2);
+    a0 = a1;
+    a1 = a2;
+    b0 = b1;
+    b1 = b2;
+}
+
+VSP_DEV void sturm_count2(const DE* de, int n, double xa, double xb, int& na, int& nb) {
+    double a0 = 1.0, a1 = de[0].d - xa;
+    double b0 = 1.0, b1 = de[0].d - xb;
+    SignCounter ca, cb;
+    ca.push(1.0, a1);
+    cb.push(1.0, b1);
+    int i = 1;
+    for (int blk = 0; i + 8 <= n; i += 8, ++blk) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sturm_step(de[i + k], xa, xb, a0, a1, b0, b1, ca, cb);
+        const double sa = rescale_factor(a0, a1), sb = rescale_factor(b0, b1);
+        a0 *= sa;
+        a1 *= sa;
+        b0 *= sb;
+        b1 *= sb;
+        if ((blk & 1) == 1) {  // 1 + 16 rows pushed at most 17..32 bits: flush before overflow
+            ca.flush();
+            cb.flush();
         }
     }
-    return c;
+    ca.flush();
+    cb.flush();
+    for (; i < n; ++i) sturm_step(de[i], xa, xb, a0, a1, b0, b1, ca, cb);
+    ca.flush();
+    cb.flush();
+    na = ca.count;
+    nb = cb.count;
 }
 
 template <class Ctx>
@@ -109,24 +145,40 @@ VSP_DEV TriInfo tri_bounds(Ctx& ctx, const double* d, const double* e, int n) {
     return t;
 }
 
-// lam[k], k = 0..n-1 ascending.  e2[] must hold squared off-diagonals.  Returns the
-// largest iteration count used by this work item.
+// lam[k], k = 0..n-1 ascending.  Work item t handles eigenvalues t and t + ceil(n/2).
+// Returns the largest iteration count used by this work item.
 template <class Ctx>
-VSP_DEV int bisect_all(Ctx& ctx, const double* d, const double* e2, int n, const TriInfo& t, double* lam) {
+VSP_DEV int bisect_all(Ctx& ctx, const DE* de, int n, const TriInfo& t, double* lam) {
     int maxit = 0;
-    for (int k = ctx.tid; k < n; k += ctx.nthreads) {
-        double lo = t.gl, hi = t.gu;
+    const int half = (n + 1) >> 1;
+    for (int k = ctx.tid; k < half; k += ctx.nthreads) {
+        const int kb = k + half;  // may be == n (odd n): then the second slot mirrors the first
+        const bool has_b = kb < n;
+        double lo_a = t.gl, hi_a = t.gu, lo_b = t.gl, hi_b = t.gu;
+        bool done_a = false, done_b = !has_b;
         int it = 0;
-        for (; it < 128; ++it) {
-            const double mid = 0.5 * (lo + hi);
-            const double tol = fmax(t.atol, 4.440892098500626e-16 * fmax(fabs(lo), fabs(hi)));
-            if (hi - lo <= tol || mid <= lo || mid >= hi) break;
-            if (sturm_count(d, e2, n, mid) >= k + 1)
-                hi = mid;
-            else
-                lo = mid;
+        for (; it < 128 && !(done_a && done_b); ++it) {
+            const double mid_a = 0.5 * (lo_a + hi_a), mid_b = 0.5 * (lo_b + hi_b);
+            if (!done_a) {
+                const double tol = fmax(t.atol, 4.440892098500626e-16 * fmax(fabs(lo_a), fabs(hi_a)));
+                done_a = (hi_a - lo_a <= tol) || mid_a <= lo_a || mid_a >= hi_a;
+            }
+            if (!done_b) {
+                const double tol = fmax(t.atol, 4.440892098500626e-16 * fmax(fabs(lo_b), fabs(hi_b)));
+                done_b = (hi_b - lo_b <= tol) || mid_b <= lo_b || mid_b >= hi_b;
+            }
+            if (done_a && done_b) break;
+            int na, nb;
+            sturm_count2(de, n, mid_a, mid_b, na, nb);
+            if (!done_a) {
+                if (na >= k + 1) hi_a = mid_a; else lo_a = mid_a;
+            }
+            if (!done_b) {
+                if (nb >= kb + 1) hi_b = mid_b; else lo_b = mid_b;
+            }
         }
-        lam[k] = 0.5 * (lo + hi);
+        lam[k] = 0.5 * (lo_a + hi_a);
+        if (has_b) lam[kb] = 0.5 * (lo_b + hi_b);
         maxit = it > maxit ? it : maxit;
     }
     return maxit;

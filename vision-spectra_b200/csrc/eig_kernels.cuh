@@ -20,7 +20,11 @@ __host__ __device__ inline size_t tridiag_global_smem_bytes(int npad) {
     return sizeof(double) * (5 * (size_t)npad + CtaCtx::kScratchDoubles);
 }
 __host__ __device__ inline size_t bisect_smem_bytes(int npad) {
-    return sizeof(double) * (3 * (size_t)npad + CtaCtx::kScratchDoubles);
+    return sizeof(double) * (5 * (size_t)npad + CtaCtx::kScratchDoubles);
+}
+__host__ __device__ inline int bisect_threads(int n) {  // two eigenvalues per thread
+    int t = (((n + 1) >> 1) + 31) & ~31;
+    return t > 1024 ? 1024 : (t < 32 ? 32 : t);
 }
 
 __global__ void tridiag_global_kernel(const ItemDesc* __restrict__ items, int item_base, double* __restrict__ ws,
@@ -80,6 +84,7 @@ __global__ void bisect_metrics_kernel(const ItemDesc* __restrict__ items, int it
     double* d = red + CtaCtx::kScratchDoubles;
     double* e = d + npad;
     double* lam = e + npad;
+    DE* de = reinterpret_cast<DE*>(lam + npad);  // (d_i, max(e_{i-1}^2, floor)) interleaved for one 16-byte load per row
     CtaCtx ctx(red);
 
     const double* __restrict__ in = ws + it.de_off;
@@ -93,10 +98,12 @@ __global__ void bisect_metrics_kernel(const ItemDesc* __restrict__ items, int it
     int iters = 0;
     if (!flags) {
         const TriInfo t = tri_bounds(ctx, d, e, n);
+        for (int i = ctx.tid; i < n; i += ctx.nthreads) {
+            de[i].d = d[i];
+            de[i].e2 = (i > 0) ? fmax(e[i - 1] * e[i - 1], kE2Floor) : 0.0;
+        }
         ctx.sync();
-        for (int i = ctx.tid; i < n; i += ctx.nthreads) e[i] = e[i] * e[i];
-        ctx.sync();
-        iters = bisect_all(ctx, d, e, n, t, lam);
+        iters = bisect_all(ctx, de, n, t, lam);
     } else {
         for (int i = ctx.tid; i < n; i += ctx.nthreads) lam[i] = 0.0;
     }

@@ -50,8 +50,9 @@ constexpr int kFusedPad = 64;  // doubles after the triangle: masked lanes may r
 // pivot row -> norm -> reflector) overlaps the other's pass: <= 113 KB of shared memory each.
 constexpr size_t kFusedSmemBudget = 113 * 1024;
 __host__ __device__ inline size_t tridiag_fused_smem_bytes(int rows_smem, int npad, int nw) {
-    // v w u p prow d e (7 npad) | pcol [nw][npad] | 2 scalars (+2 pad) | A (rows < rows_smem) + pad
-    return sizeof(double) * ((size_t)poff(rows_smem) + kFusedPad + (size_t)(7 + nw) * npad + 4);
+    // v w u p prow diag d e (8 npad) | pcol [nw][npad] | fold buffers [nw][8*34] | scalars (4) |
+    // A (rows < rows_smem) + pad
+    return sizeof(double) * ((size_t)poff(rows_smem) + kFusedPad + (size_t)(8 + nw) * npad + (size_t)nw * 8 * 34 + 4);
 }
 // Rows [0, rows_smem) of the triangle live in shared memory; the rest (the rows eliminated
 // first) stay in the global workspace and are updated in place through L2.  Even, so that a
@@ -72,35 +73,30 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// rs[0..7] hold one partial per row and lane.  On return rs[0] is the full sum of row
-// j = 4*bit4(lane) + 2*bit3(lane) + bit2(lane), identical in the 4 lanes that share j.
-__device__ __forceinline__ void fold8(double (&rs)[8], int lane) {
-    {
-        const bool hi = lane & 16;
+// Reduce 8 per-lane row partials through a per-warp shared-memory transpose: every lane
+// stores its 8 partials (row-slot major, stride 34 keeps both the stores and the transposed
+// loads bank-conflict free), then lane l sums 8 of the 32 partials of row slot k = l & 7 and
+// two butterfly steps finish the job.  ~30 instructions per 8 rows; the register-only folding
+// butterfly needs ~95 because every step has to select which half to send.
+// On return the lanes with the same (lane & 7) hold the full sum of row slot k = lane & 7.
+constexpr int kFoldStride = 34;
+constexpr int kFoldDoubles = 8 * kFoldStride;
+__device__ __forceinline__ double fold8(const double (&rs)[8], int lane, double* __restrict__ buf) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const double send = hi ? rs[k] : rs[k + 4];
-            const double keep = hi ? rs[k + 4] : rs[k];
-            rs[k] = keep + shfl_xor_d(send, 16);
-        }
-    }
-    {
-        const bool hi = lane & 8;
+    for (int k = 0; k < 8; ++k) buf[k * kFoldStride + lane] = rs[k];
+    __syncwarp();
+    const double* src = buf + (lane & 7) * kFoldStride + (lane >> 3);
+    double s = 0.0, t = 0.0;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const double send = hi ? rs[k] : rs[k + 2];
-            const double keep = hi ? rs[k + 2] : rs[k];
-            rs[k] = keep + shfl_xor_d(send, 8);
-        }
+    for (int i = 0; i < 8; i += 2) {
+        s += src[4 * i];
+        t += src[4 * (i + 1)];
     }
-    {
-        const bool hi = lane & 4;
-        const double send = hi ? rs[0] : rs[1];
-        const double keep = hi ? rs[1] : rs[0];
-        rs[0] = keep + shfl_xor_d(send, 4);
-    }
-    rs[0] += shfl_xor_d(rs[0], 2);
-    rs[0] += shfl_xor_d(rs[0], 1);
+    s += t;
+    __syncwarp();  // the buffer is reused by the next group of rows
+    s += shfl_xor_d(s, 8);
+    s += shfl_xor_d(s, 16);
+    return s;
 }
 
 // 1/x and 1/sqrt(x) for normal positive doubles: hardware seed + two Newton steps
@@ -128,7 +124,7 @@ __device__ __forceinline__ void pair_pass(double* __restrict__ row0, int r0, int
                                           double ur0, double vr1, double wr1, double ur1,
                                           const double2 (&vq)[NP], const double2 (&wq)[NP],
                                           const double2 (&uq)[NP], double2 (&colacc)[NP], double& rs0,
-                                          double& rs1) {
+                                          double& rs1, double* __restrict__ diag) {
     double* __restrict__ row1 = row0 + (r0 + 2);
     const int r1 = r0 + 1;
     double2 a0[QC], a1[QC];
@@ -167,17 +163,18 @@ __device__ __forceinline__ void pair_pass(double* __restrict__ row0, int r0, int
     {
         constexpr int q = QC - 1;
         const int c1 = c0 + 1;
-        // row part: columns <= r ; column part: columns < r (the diagonal counts once)
+        // One mask per element (columns <= r).  The diagonal therefore enters both the row sum
+        // and the column sum; the owner lane publishes it and phase (3) subtracts diag_c * u_c.
+        // r0 is even and c0 is even, so the diagonals sit at (row0, c0 == r0).x and (row1, c0 == r0).y.
         const double r0x = (c0 <= r0) ? a0[q].x : 0.0, r0y = (c1 <= r0) ? a0[q].y : 0.0;
         const double r1x = (c0 <= r1) ? a1[q].x : 0.0, r1y = (c1 <= r1) ? a1[q].y : 0.0;
-        const double k0x = (c0 < r0) ? a0[q].x : 0.0, k0y = (c1 < r0) ? a0[q].y : 0.0;
-        const double k1x = (c0 < r1) ? a1[q].x : 0.0, k1y = (c1 < r1) ? a1[q].y : 0.0;
+        if (c0 == r0) *reinterpret_cast<double2*>(diag + r0) = make_double2(a0[q].x, a1[q].y);
         s0x = fma(r0x, uq[q].x, s0x);
         s0y = fma(r0y, uq[q].y, s0y);
         s1x = fma(r1x, uq[q].x, s1x);
         s1y = fma(r1y, uq[q].y, s1y);
-        colacc[q].x = fma(k1x, ur1, fma(k0x, ur0, colacc[q].x));
-        colacc[q].y = fma(k1y, ur1, fma(k0y, ur0, colacc[q].y));
+        colacc[q].x = fma(r1x, ur1, fma(r0x, ur0, colacc[q].x));
+        colacc[q].y = fma(r1y, ur1, fma(r0y, ur0, colacc[q].y));
     }
     rs0 = s0x + s0y;
     rs1 = s1x + s1y;
@@ -188,8 +185,8 @@ __device__ __forceinline__ void pair_dispatch(double* __restrict__ row0, int r0,
                                               double ur0, double vr1, double wr1, double ur1,
                                               const double2 (&vq)[NP], const double2 (&wq)[NP],
                                               const double2 (&uq)[NP], double2 (&colacc)[NP], double& rs0,
-                                              double& rs1) {
-#define VSP_PAIR_ARGS row0, r0, lane, vr0, wr0, ur0, vr1, wr1, ur1, vq, wq, uq, colacc, rs0, rs1
+                                              double& rs1, double* __restrict__ diag) {
+#define VSP_PAIR_ARGS row0, r0, lane, vr0, wr0, ur0, vr1, wr1, ur1, vq, wq, uq, colacc, rs0, rs1, diag
     switch ((r0 + 1) >> 6) {  // warp-uniform: chunk pair that holds the diagonals
         case 0: pair_pass<NP, 1>(VSP_PAIR_ARGS); return;
         case 1: if constexpr (NP >= 2) pair_pass<NP, 2>(VSP_PAIR_ARGS); return;
@@ -215,10 +212,12 @@ __global__ void __launch_bounds__(256, 2)
     double* u = w + npad;       // current reflector vector
     double* p = u + npad;       // tau * A u
     double* prow = p + npad;    // lower-triangle row sums of A u
-    double* d = prow + npad;
+    double* diag = prow + npad;  // current diagonal, for the diagonal correction in (3)
+    double* d = diag + npad;
     double* e = d + npad;
-    double* pcol = e + npad;                  // [NW][npad] per-warp column sums
-    double* scal = pcol + (size_t)NW * npad;  // [0] tau of the current step
+    double* pcol = e + npad;                          // [NW][npad] per-warp column sums
+    double* foldbuf = pcol + (size_t)NW * npad;       // [NW][kFoldDoubles]
+    double* scal = foldbuf + (size_t)NW * kFoldDoubles;  // [0] tau of the current step
     double* A = scal + 4;                     // rows < rows_smem (+ kFusedPad)
 
     // ---- load + condition the Gram matrix: power-of-four scale so that |G_ij| <= 1 and the
@@ -406,17 +405,16 @@ __global__ void __launch_bounds__(256, 2)
                     const int off = poff(r0);
                     if (r0 < rows_smem)
                         pair_dispatch<NP>(A + off, r0, lane, vr0, wr0, ur0, vr1, wr1, ur1, vq, wq, uq, colacc,
-                                          rs[2 * j], rs[2 * j + 1]);
+                                          rs[2 * j], rs[2 * j + 1], diag);
                     else
                         pair_dispatch<NP>(G + off, r0, lane, vr0, wr0, ur0, vr1, wr1, ur1, vq, wq, uq, colacc,
-                                          rs[2 * j], rs[2 * j + 1]);
+                                          rs[2 * j], rs[2 * j + 1], diag);
                 }
             }
-            fold8(rs, lane);
-            if ((lane & 3) == 0) {
-                const int k = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);  // rs slot
-                const int r = 2 * (p0 + (k >> 1) * NW) + (k & 1);
-                if (r < m) prow[r] = rs[0];
+            const double rsum = fold8(rs, lane, foldbuf + warp * kFoldDoubles);
+            if (lane < 8) {  // lane = row slot
+                const int r = 2 * (p0 + (lane >> 1) * NW) + (lane & 1);
+                if (r < m) prow[r] = rsum;
             }
         }
 #pragma unroll
@@ -427,7 +425,7 @@ __global__ void __launch_bounds__(256, 2)
 
         // ---- (3) p = tau (A u), one column per thread
         for (int c = tid; c < m; c += nthreads) {
-            double s0 = prow[c], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            double s0 = prow[c], s1 = -diag[c] * u[c], s2 = 0.0, s3 = 0.0;  // the diagonal counted twice
             int k = 0;
             for (; k + 3 < NW; k += 4) {
                 s0 += pcol[k * npad + c];

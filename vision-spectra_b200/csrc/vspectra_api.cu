@@ -298,7 +298,7 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
         g_launches++;
         VSP_CUDA(cudaGetLastError());
         if ((rc = mark()) != VSP_OK) return rc;
-        const int bthreads = std::min(1024, c.npad);
+        const int bthreads = bisect_threads(c.n);
         bisect_metrics_kernel<<<c.count, bthreads, bisect_smem_bytes(c.npad), st>>>(p->d_items, c.begin, ws, c.npad,
                                                                                     p->opts, d_sv, d_records);
         g_launches++;

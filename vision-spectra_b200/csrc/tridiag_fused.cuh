@@ -50,9 +50,10 @@ constexpr int kFusedPad = 64;  // doubles after the triangle: masked lanes may r
 // pivot row -> norm -> reflector) overlaps the other's pass: <= 113 KB of shared memory each.
 constexpr size_t kFusedSmemBudget = 113 * 1024;
 __host__ __device__ inline size_t tridiag_fused_smem_bytes(int rows_smem, int npad, int nw) {
-    // v w u p prow diag d e (8 npad) | pcol [nw][npad] | fold buffers [nw][8*34] | scalars (4) |
+    // v w u p prow diag d e (8 npad) | pcol [nw][pstride] (doubles as the fold buffer) | scalars (4) |
     // A (rows < rows_smem) + pad
-    return sizeof(double) * ((size_t)poff(rows_smem) + kFusedPad + (size_t)(8 + nw) * npad + (size_t)nw * 8 * 34 + 4);
+    const size_t pstride = npad > 8 * 34 ? npad : 8 * 34;
+    return sizeof(double) * ((size_t)poff(rows_smem) + kFusedPad + (size_t)8 * npad + (size_t)nw * pstride + 4);
 }
 // Rows [0, rows_smem) of the triangle live in shared memory; the rest (the rows eliminated
 // first) stay in the global workspace and are updated in place through L2.  Even, so that a
@@ -215,9 +216,11 @@ __global__ void __launch_bounds__(256, 2)
     double* diag = prow + npad;  // current diagonal, for the diagonal correction in (3)
     double* d = diag + npad;
     double* e = d + npad;
-    double* pcol = e + npad;                          // [NW][npad] per-warp column sums
-    double* foldbuf = pcol + (size_t)NW * npad;       // [NW][kFoldDoubles]
-    double* scal = foldbuf + (size_t)NW * kFoldDoubles;  // [0] tau of the current step
+    // [NW][pstride] per-warp column sums, written at the end of the pass; during the pass the
+    // same row is this warp's fold buffer
+    const int pstride = npad > kFoldDoubles ? npad : kFoldDoubles;
+    double* pcol = e + npad;
+    double* scal = pcol + (size_t)NW * pstride;  // [0] tau of the current step
     double* A = scal + 4;                     // rows < rows_smem (+ kFusedPad)
 
     // ---- load + condition the Gram matrix: power-of-four scale so that |G_ij| <= 1 and the
@@ -411,7 +414,7 @@ __global__ void __launch_bounds__(256, 2)
                                           rs[2 * j], rs[2 * j + 1], diag);
                 }
             }
-            const double rsum = fold8(rs, lane, foldbuf + warp * kFoldDoubles);
+            const double rsum = fold8(rs, lane, pcol + warp * pstride);
             if (lane < 8) {  // lane = row slot
                 const int r = 2 * (p0 + (lane >> 1) * NW) + (lane & 1);
                 if (r < m) prow[r] = rsum;
@@ -419,7 +422,7 @@ __global__ void __launch_bounds__(256, 2)
         }
 #pragma unroll
         for (int q = 0; q < NP; ++q)
-            if (64 * q < m) *reinterpret_cast<double2*>(pcol + warp * npad + 2 * lane + 64 * q) = colacc[q];
+            if (64 * q < m) *reinterpret_cast<double2*>(pcol + warp * pstride + 2 * lane + 64 * q) = colacc[q];
         VSP_LAP(1);
         __syncthreads();
 
@@ -428,12 +431,12 @@ __global__ void __launch_bounds__(256, 2)
             double s0 = prow[c], s1 = -diag[c] * u[c], s2 = 0.0, s3 = 0.0;  // the diagonal counted twice
             int k = 0;
             for (; k + 3 < NW; k += 4) {
-                s0 += pcol[k * npad + c];
-                s1 += pcol[(k + 1) * npad + c];
-                s2 += pcol[(k + 2) * npad + c];
-                s3 += pcol[(k + 3) * npad + c];
+                s0 += pcol[k * pstride + c];
+                s1 += pcol[(k + 1) * pstride + c];
+                s2 += pcol[(k + 2) * pstride + c];
+                s3 += pcol[(k + 3) * pstride + c];
             }
-            for (; k < NW; ++k) s0 += pcol[k * npad + c];
+            for (; k < NW; ++k) s0 += pcol[k * pstride + c];
             p[c] = tau * ((s0 + s1) + (s2 + s3));
         }
         VSP_LAP(2);

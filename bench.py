@@ -249,7 +249,18 @@ def run_b200_arm(args) -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL writes its version banner to stdout on first use; keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier(device_ids=[local])
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     lay = CheckpointLayout.vit(SCENARIO["embed_dim"], SCENARIO["depth"])
     n_ckpt = args.ckpts
@@ -337,11 +348,11 @@ def run_b200_arm(args) -> None:
 
     # ---------------- roofline of the dominant kernel
     peaks = load_peaks()
-    names = ["gram_f64_kernel", "tridiag_smem_kernel", "bisect_metrics_kernel"]
+    names = ["gram_f64_kernel", "tridiag_fused_kernel", "bisect_metrics_kernel"]
     alg = {
         "gram_f64_kernel": {"bound": "hbm", "work": in_bytes / 1e9, "unit": "GB/s", "peak": peaks["hbm_gbs"],
                             "flops": n_ckpt * lay.flops_gram()},
-        "tridiag_smem_kernel": {"bound": "fp64", "work": n_ckpt * lay.flops_tridiag() / 1e12, "unit": "TFLOP/s",
+        "tridiag_fused_kernel": {"bound": "fp64", "work": n_ckpt * lay.flops_tridiag() / 1e12, "unit": "TFLOP/s",
                                 "peak": FP64_PEAK_TFLOPS},
         "bisect_metrics_kernel": {"bound": "fp64", "work": None, "unit": "TFLOP/s", "peak": FP64_PEAK_TFLOPS},
     }

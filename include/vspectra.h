@@ -133,6 +133,11 @@ int vsp_plan_execute_profiled(vsp_plan* plan, const void* const* d_ptrs, double*
                               vsp_record* d_records, void* d_workspace, int64_t workspace_bytes,
                               void* stream, float* stage_ms /* [3] */);
 
+/* Validation aid: run stage 1 only and expand every Gram matrix (smaller side, f64) into a
+ * dense n*n block of d_out (blocks in batch order, n_i*n_i doubles each).  Synchronises. */
+int vsp_plan_debug_gram(vsp_plan* plan, const void* const* d_ptrs, double* d_out, void* d_workspace,
+                        int64_t workspace_bytes, void* stream);
+
 /* One-shot form of create + execute + destroy. */
 int vsp_analyze_batch(const void* const* d_ptrs, const int32_t* rows, const int32_t* cols,
                       const int64_t* ld, int32_t dtype, int32_t count, const vsp_opts* opts,

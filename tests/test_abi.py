@@ -30,7 +30,7 @@ def test_every_declared_symbol_is_exported(lib):
     from vision_spectra_b200 import _native as nat
 
     declared = _declared_functions()
-    assert len(declared) >= 14
+    assert len(declared) >= 16
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/vspectra.h but not exported"
     assert sorted(nat.EXPORTED_SYMBOLS) == declared
@@ -57,15 +57,17 @@ def test_shape_validation_and_layout_queries(lib):
 
     rows, cols = nat.i32([32, 128, 32, 768]), nat.i32([32, 32, 128, 3072])
     ws = lib.vsp_workspace_bytes(4, nat.p32(rows), nat.p32(cols))
-    expect = sum(((n * (n + 1) // 2 + (n + 1) // 2 + 3) // 4 * 4 if n <= 256 else n * n) + (2 * n + 4 + 3) // 4 * 4 for n in (32, 32, 32, 768))
-    assert ws == expect * 8 + 1024
+    r1k = lambda v: (v + 1023) // 1024 * 1024
+    f64 = sum(((n * (n + 1) // 2 + (n + 1) // 2 + 3) // 4 * 4 if n <= 256 else n * n) + (2 * n + 4 + 3) // 4 * 4 for n in (32, 32, 32, 768))
+    i8 = sum(r1k(6 * n * ((k + 63) // 64 * 64)) + r1k(4 * n) for n, k in ((32, 32), (32, 128), (32, 128), (768, 3072)))
+    assert ws == r1k(f64 * 8) + i8 + 2048
     offs = np.zeros(5, np.int64)
     assert lib.vsp_sv_offsets(4, nat.p32(rows), nat.p32(cols), nat.p64(offs)) == 0
     assert offs.tolist() == [0, 32, 64, 96, 864]
     assert lib.vsp_workspace_bytes(-1, nat.p32(rows), nat.p32(cols)) == -1
     assert lib.vsp_workspace_bytes(4, nat.p32(nat.i32([0, 1, 1, 1])), nat.p32(cols)) == -1
     assert lib.vsp_workspace_bytes(1, nat.p32(nat.i32([5000])), nat.p32(nat.i32([6000]))) == -2
-    assert lib.vsp_workspace_bytes(0, None, None) == 1024
+    assert lib.vsp_workspace_bytes(0, None, None) == 2048
 
 
 def test_no_cpu_fallback_without_gpu():

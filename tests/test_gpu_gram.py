@@ -1,0 +1,77 @@
+"""Stage 1 in isolation: the tcgen05 int8-split Gram (fp32 inputs) and the FP64 CUDA-core
+Gram (fp64 inputs) against torch's float64 matmul.  The split is exact up to 2^-46, so the
+tolerance is FP64-level (1e-13 relative to sqrt(G_ii G_jj))."""
+
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _gram_via_abi(mats):
+    from vision_spectra_b200 import _native as nat
+
+    lib = nat.load()
+    dev = mats[0].device
+    count = len(mats)
+    rows, cols = nat.i32([m.shape[0] for m in mats]), nat.i32([m.shape[1] for m in mats])
+    ld = nat.i64([m.stride(0) for m in mats])
+    dtype = nat.VSP_F32 if mats[0].dtype == torch.float32 else nat.VSP_F64
+    plan = ctypes.c_void_p()
+    nat.check(lib.vsp_plan_create(count, nat.p32(rows), nat.p32(cols), nat.p64(ld), dtype, None, ctypes.byref(plan)))
+    ws = torch.empty(int(lib.vsp_plan_workspace_bytes(plan)), dtype=torch.uint8, device=dev)
+    ns = np.minimum(rows, cols).astype(np.int64)
+    out = torch.full((int((ns * ns).sum()),), float("nan"), dtype=torch.float64, device=dev)
+    ptrs = (ctypes.c_void_p * count)(*[m.data_ptr() for m in mats])
+    nat.check(lib.vsp_plan_debug_gram(plan, ptrs, out.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    lib.vsp_plan_destroy(plan)
+    res, off = [], 0
+    for n in ns:
+        res.append(out[off : off + n * n].view(n, n).cpu().numpy())
+        off += n * n
+    return res
+
+
+def _ref_gram(m):
+    x = m.double()
+    return (x @ x.T if m.shape[0] <= m.shape[1] else x.T @ x).cpu().numpy()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_gram_matches_float64_matmul(dtype):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    shapes = [(32, 32), (128, 32), (32, 128), (96, 96), (384, 96), (96, 384), (192, 192), (768, 192), (192, 768),
+              (7, 7), (9, 33), (257, 65), (200, 130), (1, 1), (100, 4), (300, 300)]
+    mats = [(torch.randn(s, generator=g, device="cuda", dtype=torch.float32) * 0.02).to(dtype) for s in shapes]
+    # rows spanning 9 decades, denormals, an exact-zero row
+    wide = torch.randn(64, 256, generator=g, device="cuda") * torch.logspace(-6, 3, 64, device="cuda")[:, None]
+    wide[5] = 0
+    tiny = torch.randn(40, 40, generator=g, device="cuda") * 1e-41
+    mats += [wide.to(dtype), tiny.float().to(dtype)]
+    got = _gram_via_abi(mats)
+    for m, G in zip(mats, got):
+        ref = _ref_gram(m)
+        dg = np.sqrt(np.maximum(np.diag(ref), 0))
+        scale = np.outer(dg, dg)
+        scale[scale == 0] = 1.0
+        err = np.max(np.abs(G - ref) / scale)
+        assert np.all(np.isfinite(G)) and err < 1e-13, (tuple(m.shape), err)
+        assert np.array_equal(G, G.T)
+
+
+def test_gram_views_and_nonfinite():
+    g = torch.Generator(device="cuda").manual_seed(2)
+    qkv = torch.randn(3 * 192, 192, generator=g, device="cuda") * 0.02
+    views = [qkv[:192], qkv[192:384], qkv[384:]]
+    col = (torch.randn(96, 200, generator=g, device="cuda") * 0.02)[:, 10:106]  # ld = 200
+    bad = torch.randn(48, 48, generator=g, device="cuda")
+    bad[3, 7] = float("inf")
+    got = _gram_via_abi(views + [col, bad])
+    for m, G in zip(views + [col], got[:4]):
+        ref = _ref_gram(m)
+        assert np.max(np.abs(G - ref)) / np.max(np.abs(ref)) < 1e-13
+    assert not np.isfinite(got[4][3, 3])  # the poisoned Gram row is flagged on the diagonal

@@ -88,6 +88,7 @@ def load() -> ctypes.CDLL:
             c_int32,
             [c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, POINTER(ctypes.c_float)],
         ),
+        "vsp_plan_debug_gram": (c_int32, [c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_int64, c_void_p]),
         "vsp_analyze_batch": (
             c_int32,
             [POINTER(c_void_p), P32, P32, P64, c_int32, c_int32, POINTER(VspOpts), c_void_p, c_void_p, c_void_p, c_int64, c_void_p],
@@ -119,6 +120,7 @@ EXPORTED_SYMBOLS = (
     "vsp_plan_destroy",
     "vsp_plan_execute",
     "vsp_plan_execute_profiled",
+    "vsp_plan_debug_gram",
     "vsp_analyze_batch",
     "vsp_analyze_batch_host",
     "vsp_kernel_launch_count",

@@ -1,0 +1,363 @@
+// gram_i8.cuh -- stage 1 for fp32 inputs on the 5th-generation tensor cores:
+// an exact ("FP32-emulated split", Ozaki-style) Gram matrix with tcgen05 / TMEM / TMA.
+//
+//   x_ik = q_ik * 2^(E_i - 167),  q_ik a 42-bit signed integer (E_i = largest biased exponent
+//   of Gram row i, so q keeps every mantissa bit of elements within 2^-17 of the row maximum
+//   and rounds smaller ones at 2^-41 of it),
+//   q = sum_{t=0..5} s_t 128^(5-t),  s_t in [-64, 64]   (balanced base-128 digits, int8),
+//   sum_k q_ik q_jk = sum_{s} 128^(10-s) P_s[i][j],   P_s = sum_{t+t'=s} S_t S_t'^T.
+//
+// Every P_s is an int8 x int8 -> int32 tensor-core product (tcgen05.mma kind::i8): exact, no
+// rounding anywhere (|P_s| <= 6 * 4096 * 64^2 < 2^27).  Levels s = 0..6 (26 digit pairs) are
+// kept: the dropped ones are below 2^-46 of the result, i.e. the Gram matrix is as accurate as
+// the FP64-accumulated one (5e-15 measured) and the 1e-5 singular-value gate survives the
+// squaring of the condition number (plain 3xTF32 does not).
+//
+// Two kernels:
+//   slice_i8_kernel    fp32 W -> row exponents E[n] and six int8 digit planes S_t[n][Kp],
+//                      K-major, K padded to a multiple of 64 with zeros (also transposes the
+//                      tall case, so the MMA kernel only ever sees K-major operands).
+//   gram_i8_mma_kernel one CTA per 128x64 output tile of the lower triangle:
+//        warp 0    TMA producer: 12 boxes per 64-byte K chunk (6 A planes 128x64B, 6 B planes
+//                  64x64B, SWIZZLE_64B) into a 3-stage shared-memory ring (mbarrier full/empty)
+//        warp 1    allocates 512 TMEM columns, one elected lane issues 26 pairs x 2
+//                  tcgen05.mma (M=128, N=64, K=32) per chunk into 7 int32 accumulators
+//                  (one per level s, 64 columns each), tcgen05.commit frees the stage
+//        warps 2-5 epilogue: tcgen05.ld the 7 levels, Horner in FP64
+//                  (acc = acc*128 + P_s), scale by 2^(E_i+E_j-306), store the packed triangle.
+#pragma once
+
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tridiag_fused.cuh"  // poff()
+
+namespace vsp {
+
+constexpr int kDigits = 6;     // int8 digit planes per matrix
+constexpr int kLevels = 7;     // P_s levels kept (s = 0..6)
+constexpr int kI8TileM = 128;  // UMMA M
+constexpr int kI8TileN = 64;   // UMMA N
+constexpr int kI8ChunkK = 64;  // bytes of K per pipeline stage (= SWIZZLE_64B span)
+constexpr int kI8Stages = 3;
+constexpr int kI8StageBytes = kDigits * (kI8TileM + kI8TileN) * kI8ChunkK;  // 73728
+constexpr int kI8SmemBytes = kI8Stages * kI8StageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kI8MaxTiles = 64;
+
+// Gram class: all items of a plan with the same (n, Kp); they share one digit-plane tensor.
+struct I8Class {
+    int n, kp;          // Gram order, padded contraction length (bytes per digit row)
+    int begin, count;   // item range in the plan's sorted item table (sorted by n, then kp)
+    int64_t slice_off;  // byte offset of the [count][6][n][kp] digit planes in the workspace
+    int64_t exp_off;    // byte offset of the [count][n] int32 row exponents
+    int ntiles;
+    unsigned char tile_m[kI8MaxTiles], tile_n[kI8MaxTiles];  // lower-triangle 128x64 tiles
+};
+
+// ---------------------------------------------------------------------------------- slicing
+__device__ __forceinline__ int f32_exp_field(unsigned bits) {
+    const int ex = (bits >> 23) & 0xff;
+    return ex ? ex : 1;  // zero / denormal: exponent field 1, no implicit bit
+}
+
+// six balanced base-128 digits of x relative to row exponent E, most significant first
+__device__ __forceinline__ void f32_digits(unsigned bits, int E, signed char (&dg)[kDigits]) {
+    const int exf = (bits >> 23) & 0xff;
+    long long man = bits & 0x7fffff;
+    if (exf) man |= 0x800000;
+    const int sh = 17 - (E - (exf ? exf : 1));
+    long long q;
+    if (sh >= 0) {
+        q = man << sh;
+    } else {
+        const int r = -sh;
+        q = (r > 40) ? 0 : ((man + (1LL << (r - 1))) >> r);
+    }
+    if (bits >> 31) q = -q;
+#pragma unroll
+    for (int t = kDigits - 1; t >= 1; --t) {
+        const long long dd = ((q + 64) & 127) - 64;
+        q = (q - dd) >> 7;
+        dg[t] = (signed char)dd;
+    }
+    dg[0] = (signed char)q;
+}
+
+// One CTA per (item, block of 32 Gram rows).  256 threads.
+//   trans == 0 : Gram row i = row i of W (contiguous K): warp per row.
+//   trans == 1 : Gram row i = column i of W: lanes on columns, digits transposed through smem.
+__global__ void __launch_bounds__(256)
+    slice_i8_kernel(const ItemDesc* __restrict__ items, I8Class cls, unsigned char* __restrict__ wsb) {
+    const ItemDesc it = items[cls.begin + blockIdx.x];
+    const int n = it.n, K = it.kdim, kp = cls.kp;
+    const int i0 = blockIdx.y * 32;
+    if (i0 >= n) return;
+    const float* __restrict__ W = reinterpret_cast<const float*>(it.ptr);
+    const int64_t ld = it.ld;
+    signed char* __restrict__ planes =
+        reinterpret_cast<signed char*>(wsb + cls.slice_off) + (int64_t)blockIdx.x * kDigits * n * kp;
+    int* __restrict__ Eout = reinterpret_cast<int*>(wsb + cls.exp_off) + (int64_t)blockIdx.x * n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int sE[32];
+    __shared__ __align__(16) signed char sdig[kDigits][32][64 + 16];
+
+    if (!it.trans) {
+        for (int r = warp; r < 32; r += 8) {
+            const int i = i0 + r;
+            if (i >= n) continue;  // warp-uniform
+            const float* row = W + (int64_t)i * ld;
+            int e = 1;
+            for (int k = lane; k < K; k += 32) {
+                const unsigned b = __float_as_uint(row[k]);
+                const int ex = (b >> 23) & 0xff;
+                e = max(e, ex ? ex : 1);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) e = max(e, __shfl_xor_sync(0xffffffffu, e, o));
+            if (lane == 0) Eout[i] = e;
+            for (int k = lane; k < kp; k += 32) {
+                signed char dg[kDigits] = {0, 0, 0, 0, 0, 0};
+                if (k < K) f32_digits(__float_as_uint(row[k]), e, dg);
+#pragma unroll
+                for (int t = 0; t < kDigits; ++t) planes[((int64_t)t * n + i) * kp + k] = dg[t];
+            }
+        }
+    } else {
+        // column maxima: warp w scans rows k = w, w+8, ...; lanes on the 32 columns of this block
+        const int i = i0 + lane;
+        int e = 1;
+        if (i < n)
+            for (int k = warp; k < K; k += 8) {
+                const unsigned b = __float_as_uint(W[(int64_t)k * ld + i]);
+                const int ex = (b >> 23) & 0xff;
+                e = max(e, ex ? ex : 1);
+            }
+        if (tid < 32) sE[tid] = 1;
+        __syncthreads();
+        atomicMax(&sE[lane], e);
+        __syncthreads();
+        if (tid < 32 && i0 + tid < n) Eout[i0 + tid] = sE[tid];
+        const int Ei = sE[lane];
+        for (int k0 = 0; k0 < kp; k0 += 64) {
+            for (int kk = warp; kk < 64; kk += 8) {
+                const int k = k0 + kk;
+                signed char dg[kDigits] = {0, 0, 0, 0, 0, 0};
+                if (k < K && i < n) f32_digits(__float_as_uint(W[(int64_t)k * ld + i]), Ei, dg);
+#pragma unroll
+                for (int t = 0; t < kDigits; ++t) sdig[t][lane][kk] = dg[t];
+            }
+            __syncthreads();
+            // 6 planes x 32 rows x 64 bytes = 768 16-byte vectors, coalesced 64-byte runs
+            for (int v = tid; v < kDigits * 32 * 4; v += 256) {
+                const int t = v / 128, r = (v >> 2) & 31, c = v & 3;
+                if (i0 + r < n)
+                    *reinterpret_cast<uint4*>(planes + ((int64_t)t * n + i0 + r) * kp + k0 + 16 * c) =
+                        *reinterpret_cast<const uint4*>(&sdig[t][r][16 * c]);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded spin: a protocol bug must end in a trap (reported as a CUDA error), never in a hang.
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    for (long long spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1LL << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+// K-major, SWIZZLE_64B operand tile: rows at 64-byte pitch, 8-row atoms of 512 bytes.
+__device__ __forceinline__ unsigned long long umma_desc_sw64(unsigned smem_addr) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((smem_addr >> 4) & 0x3fff);  // start address
+    d |= (unsigned long long)1 << 16;                       // leading byte offset (unused for swizzled K-major)
+    d |= (unsigned long long)(512 >> 4) << 32;              // stride byte offset: next 8-row atom
+    d |= (unsigned long long)1 << 46;                       // descriptor version (Blackwell)
+    d |= (unsigned long long)4 << 61;                       // layout type SWIZZLE_64B
+    return d;
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, int8 x int8 -> int32, M=128, N=64, K=32
+__device__ __forceinline__ void umma_i8(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                        unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, int (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+// ------------------------------------------------------------------------------------- MMA
+__global__ void __launch_bounds__(192, 1)
+    gram_i8_mma_kernel(const ItemDesc* __restrict__ items, I8Class cls, unsigned char* __restrict__ wsb,
+                       double* __restrict__ ws, const __grid_constant__ CUtensorMap tmA,
+                       const __grid_constant__ CUtensorMap tmB) {
+    extern __shared__ unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const ItemDesc it = items[cls.begin + blockIdx.x];
+    const int n = it.n;
+    const int mt = cls.tile_m[blockIdx.y], nt = cls.tile_n[blockIdx.y];
+    const int nchunks = cls.kp / kI8ChunkK;
+
+    unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(tiles + kI8Stages * kI8StageBytes);
+    // bars[0..2] full, bars[3..5] empty, bars[6] accumulators ready; then the TMEM base address
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 8);
+    const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + kI8Stages), accbar = smem_u32(bars + 2 * kI8Stages);
+
+    if (tid == 0) {
+        for (int s = 0; s < kI8Stages; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(accbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // whole warp: allocate all 512 TMEM columns (7 levels x 64 used)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const int rowA = blockIdx.x * kDigits * n + mt * kI8TileM;  // + t*n per digit plane
+            const int rowB = blockIdx.x * kDigits * n + nt * kI8TileN;
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % kI8Stages;
+                if (c >= kI8Stages) mbar_wait(empty0 + 8 * s, ((c / kI8Stages) - 1) & 1);
+                mbar_expect_tx(full0 + 8 * s, kI8StageBytes);
+                const unsigned base = smem_u32(tiles + s * kI8StageBytes);
+#pragma unroll
+                for (int t = 0; t < kDigits; ++t) {
+                    tma_load_2d(base + t * (kI8TileM * kI8ChunkK), &tmA, full0 + 8 * s, c * kI8ChunkK, rowA + t * n);
+                    tma_load_2d(base + kDigits * kI8TileM * kI8ChunkK + t * (kI8TileN * kI8ChunkK), &tmB,
+                                full0 + 8 * s, c * kI8ChunkK, rowB + t * n);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // instruction descriptor: D = S32, A = B = signed int8, both K-major, N = 64, M = 128
+            const unsigned idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(kI8TileN >> 3) << 17) |
+                                   ((unsigned)(kI8TileM >> 4) << 24);
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % kI8Stages;
+                mbar_wait(full0 + 8 * s, (c / kI8Stages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned baseA = smem_u32(tiles + s * kI8StageBytes);
+                const unsigned baseB = baseA + kDigits * kI8TileM * kI8ChunkK;
+#pragma unroll
+                for (int lv = 0; lv < kLevels; ++lv) {
+                    const int tlo = lv > kDigits - 1 ? lv - (kDigits - 1) : 0;
+                    const int thi = lv < kDigits - 1 ? lv : kDigits - 1;
+                    for (int t = tlo; t <= thi; ++t) {
+                        const unsigned long long ad = umma_desc_sw64(baseA + t * (kI8TileM * kI8ChunkK));
+                        const unsigned long long bd = umma_desc_sw64(baseB + (lv - t) * (kI8TileN * kI8ChunkK));
+#pragma unroll
+                        for (int ks = 0; ks < kI8ChunkK / 32; ++ks) {
+                            const unsigned acc = (c > 0 || t > tlo || ks > 0) ? 1u : 0u;
+                            umma_i8(tmem_base + lv * kI8TileN, ad + 2 * ks, bd + 2 * ks, idesc, acc);
+                        }
+                    }
+                }
+                umma_commit(empty0 + 8 * s);  // the stage is free once these MMAs have read it
+            }
+            umma_commit(accbar);
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
+        const int q = warp & 3;
+        const int i = mt * kI8TileM + 32 * q + lane;  // Gram row of this thread
+        const int* __restrict__ E = reinterpret_cast<const int*>(wsb + cls.exp_off) + (int64_t)blockIdx.x * n;
+        const int Ei = (i < n) ? E[i] : 1;
+        double* __restrict__ G = ws + it.gram_off;
+        mbar_wait(accbar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int cc = 0; cc < kI8TileN / 16; ++cc) {
+            double acc[16];
+            int r[16];
+            const unsigned taddr = tmem_base + ((unsigned)(32 * q) << 16) + cc * 16;
+            tmem_ld16(taddr, r);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc[k] = (double)r[k];
+#pragma unroll
+            for (int lv = 1; lv < kLevels; ++lv) {
+                tmem_ld16(taddr + lv * kI8TileN, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int k = 0; k < 16; ++k) acc[k] = fma(acc[k], 128.0, (double)r[k]);
+            }
+            if (i < n) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int j = nt * kI8TileN + cc * 16 + k;
+                    if (j <= i) {
+                        const int Ej = E[j];
+                        double g;
+                        if (Ei == 255 || Ej == 255) {
+                            g = __longlong_as_double(0x7ff8000000000000LL);  // NaN/Inf in the input row
+                        } else {
+                            // sum_k q_i q_j = 128^4 * acc ; x = q 2^(E-167)  ->  2^(Ei+Ej-334+28)
+                            const int be = Ei + Ej - 306 + 1023;
+                            g = acc[k] * __hiloint2double(be << 20, 0);
+                        }
+                        if (it.full) {
+                            G[(int64_t)i * n + j] = g;
+                            G[(int64_t)j * n + i] = g;
+                        } else {
+                            G[poff(i) + j] = g;
+                        }
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+}  // namespace vsp

@@ -18,6 +18,7 @@
 
 #include "eig_kernels.cuh"
 #include "gram_f64.cuh"
+#include "gram_i8.cuh"
 
 using namespace vsp;
 
@@ -67,6 +68,9 @@ struct vsp_plan {
     std::vector<ItemDesc> items;  // sorted by shape class
     std::vector<int> order;       // sorted position -> caller index
     std::vector<ShapeClass> classes;
+    std::vector<I8Class> i8classes;  // fp32 inputs: (n, Kp) groups sharing one digit-plane tensor
+    int64_t i8_bytes = 0;            // digit planes + row exponents, after the FP64 region
+    int gram_method = 1;             // 1: tcgen05 int8 split (fp32 inputs), 0: FP64 CUDA cores
     int64_t ws_doubles = 0;
     int64_t sv_total = 0;
     ItemDesc* d_items = nullptr;
@@ -74,6 +78,67 @@ struct vsp_plan {
 };
 
 namespace {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<PFN_encodeTiled>(f);
+    }();
+    return fn;
+}
+
+// digit planes of one Gram class as a 2-D uint8 tensor [count*6*n rows][kp bytes], 64-byte swizzle
+int make_plane_map(CUtensorMap* map, void* base, const I8Class& c, int box_rows) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) {
+        t_cuda_error = "cuTensorMapEncodeTiled entry point not available";
+        return VSP_E_CUDA;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)c.kp, (cuuint64_t)c.count * kDigits * c.n};
+    const cuuint64_t strides[1] = {(cuuint64_t)c.kp};
+    const cuuint32_t box[2] = {(cuuint32_t)kI8ChunkK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        t_cuda_error = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")";
+        return VSP_E_CUDA;
+    }
+    return VSP_OK;
+}
+
+// stage 1 on the tensor cores for every (n, Kp) group of this shape class
+int launch_gram_i8(const vsp_plan* p, const ShapeClass& c, double* ws, unsigned char* wsb, cudaStream_t st) {
+    for (const I8Class& g : p->i8classes) {
+        if (g.n != c.n) continue;
+        dim3 sgrid(g.count, (g.n + 31) / 32);
+        slice_i8_kernel<<<sgrid, 256, 0, st>>>(p->d_items, g, wsb);
+        g_launches++;
+        if (!cuda_ok(cudaGetLastError(), "slice_i8_kernel")) return VSP_E_CUDA;
+        CUtensorMap tmA, tmB;
+        int rc = make_plane_map(&tmA, wsb + g.slice_off, g, kI8TileM);
+        if (rc == VSP_OK) rc = make_plane_map(&tmB, wsb + g.slice_off, g, kI8TileN);
+        if (rc != VSP_OK) return rc;
+        if (!cuda_ok(cudaFuncSetAttribute(gram_i8_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kI8SmemBytes),
+                     "cudaFuncSetAttribute(gram_i8_mma_kernel)"))
+            return VSP_E_CUDA;
+        dim3 mgrid(g.count, g.ntiles);
+        gram_i8_mma_kernel<<<mgrid, 192, kI8SmemBytes, st>>>(p->d_items, g, wsb, ws, tmA, tmB);
+        g_launches++;
+        if (!cuda_ok(cudaGetLastError(), "gram_i8_mma_kernel")) return VSP_E_CUDA;
+    }
+    return VSP_OK;
+}
+
 template <typename TIn>
 int launch_gram(const vsp_plan* p, const ShapeClass& c, double* ws, cudaStream_t st) {
     if (c.n <= 32) {
@@ -132,12 +197,15 @@ static int64_t item_ws_doubles(int n, int full) {
 int64_t vsp_workspace_bytes(int32_t count, const int32_t* rows, const int32_t* cols) {
     const int rc = validate(count, rows, cols, nullptr);
     if (rc != VSP_OK) return rc;
-    int64_t total = 0;
+    int64_t total = 0, i8 = 0;
     for (int i = 0; i < count; ++i) {
         const int n = std::min(rows[i], cols[i]);
         total += item_ws_doubles(n, n > kSmemMaxN);
+        // fp32 inputs: six int8 digit planes [n][Kp] + row exponents (upper bound: per-item rounding)
+        i8 += round_up64((int64_t)kDigits * n * round_up(std::max(rows[i], cols[i]), kI8ChunkK), 1024) +
+              round_up64((int64_t)n * 4, 1024);
     }
-    return total * (int64_t)sizeof(double) + 1024;
+    return round_up64(total * (int64_t)sizeof(double), 1024) + i8 + 2048;
 }
 
 int vsp_plan_create(int32_t count, const int32_t* rows, const int32_t* cols, const int64_t* ld, int32_t dtype,
@@ -166,7 +234,9 @@ int vsp_plan_create(int32_t count, const int32_t* rows, const int32_t* cols, con
     p->order.resize(count);
     for (int i = 0; i < count; ++i) p->order[i] = i;
     std::stable_sort(p->order.begin(), p->order.end(), [&](int a, int b) {
-        return std::min(rows[a], cols[a]) < std::min(rows[b], cols[b]);
+        const int na = std::min(rows[a], cols[a]), nb = std::min(rows[b], cols[b]);
+        if (na != nb) return na < nb;
+        return std::max(rows[a], cols[a]) < std::max(rows[b], cols[b]);
     });
     p->items.resize(count);
     int64_t off = 0;
@@ -201,6 +271,41 @@ int vsp_plan_create(int32_t count, const int32_t* rows, const int32_t* cols, con
         p->classes.back().count++;
     }
     p->ws_doubles = off;
+    {   // tuning / fallback switch: VSP_GRAM=f64 selects the FP64 CUDA-core Gram for fp32 inputs too
+        const char* e = std::getenv("VSP_GRAM");
+        p->gram_method = (e && std::string(e) == "f64") ? 0 : 1;
+    }
+    if (dtype == VSP_F32 && p->gram_method == 1) {
+        int64_t boff = 0;
+        for (int s = 0; s < count; ++s) {
+            const ItemDesc& it = p->items[s];
+            const int kp = round_up(it.kdim, kI8ChunkK);
+            if (p->i8classes.empty() || p->i8classes.back().n != it.n || p->i8classes.back().kp != kp) {
+                I8Class c{};
+                c.n = it.n;
+                c.kp = kp;
+                c.begin = s;
+                c.count = 0;
+                c.ntiles = 0;
+                for (int mt = 0; mt * kI8TileM < it.n; ++mt)
+                    for (int nt = 0; nt * kI8TileN < it.n && nt * kI8TileN <= mt * kI8TileM + kI8TileM - 1; ++nt)
+                        if (c.ntiles < kI8MaxTiles) {
+                            c.tile_m[c.ntiles] = (unsigned char)mt;
+                            c.tile_n[c.ntiles] = (unsigned char)nt;
+                            c.ntiles++;
+                        }
+                p->i8classes.push_back(c);
+            }
+            p->i8classes.back().count++;
+        }
+        for (I8Class& c : p->i8classes) {
+            c.slice_off = boff;
+            boff += round_up64((int64_t)c.count * kDigits * c.n * c.kp, 1024);
+            c.exp_off = boff;
+            boff += round_up64((int64_t)c.count * c.n * 4, 1024);
+        }
+        p->i8_bytes = boff;
+    }
     if (count > 0) {
         if (!cuda_ok(cudaGetDevice(&p->device), "cudaGetDevice") ||
             !cuda_ok(cudaMalloc(&p->d_items, sizeof(ItemDesc) * (size_t)count), "cudaMalloc(items)")) {
@@ -212,8 +317,10 @@ int vsp_plan_create(int32_t count, const int32_t* rows, const int32_t* cols, con
     return VSP_OK;
 }
 
+static int64_t plan_f64_bytes(const vsp_plan* plan) { return round_up64(plan->ws_doubles * (int64_t)sizeof(double), 1024); }
+
 int64_t vsp_plan_workspace_bytes(const vsp_plan* plan) {
-    return plan ? plan->ws_doubles * (int64_t)sizeof(double) + 1024 : VSP_E_ARG;
+    return plan ? plan_f64_bytes(plan) + plan->i8_bytes + 2048 : VSP_E_ARG;
 }
 int64_t vsp_plan_sv_count(const vsp_plan* plan) { return plan ? plan->sv_total : VSP_E_ARG; }
 
@@ -232,7 +339,7 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
     // align the workspace to 256 bytes inside the caller's buffer
     uintptr_t base = reinterpret_cast<uintptr_t>(d_workspace);
     uintptr_t aligned = (base + 255) & ~uintptr_t(255);
-    if ((int64_t)(aligned - base) + p->ws_doubles * (int64_t)sizeof(double) > workspace_bytes) return VSP_E_WORKSPACE;
+    if ((int64_t)(aligned - base) + plan_f64_bytes(p) + p->i8_bytes > workspace_bytes) return VSP_E_WORKSPACE;
     double* ws = reinterpret_cast<double*>(aligned);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
@@ -258,7 +365,10 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
     for (const ShapeClass& c : p->classes) {
         int rc = mark();
         if (rc != VSP_OK) return rc;
-        rc = (p->dtype == VSP_F32) ? launch_gram<float>(p, c, ws, st) : launch_gram<double>(p, c, ws, st);
+        if (p->dtype == VSP_F32 && p->gram_method == 1)
+            rc = launch_gram_i8(p, c, ws, reinterpret_cast<unsigned char*>(ws) + plan_f64_bytes(p), st);
+        else
+            rc = (p->dtype == VSP_F32) ? launch_gram<float>(p, c, ws, st) : launch_gram<double>(p, c, ws, st);
         if (rc != VSP_OK) return rc;
         if ((rc = mark()) != VSP_OK) return rc;
         if (!c.full) {
@@ -305,6 +415,56 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
         VSP_CUDA(cudaGetLastError());
         if ((rc = mark()) != VSP_OK) return rc;
     }
+    return VSP_OK;
+}
+
+// expand item `blockIdx.x`'s Gram matrix (packed padded rows or full) into a dense n x n block
+__global__ void expand_gram_kernel(const ItemDesc* __restrict__ items, const double* __restrict__ ws,
+                                   const int64_t* __restrict__ out_off, double* __restrict__ out) {
+    const ItemDesc it = items[blockIdx.x];
+    const int n = it.n;
+    const double* G = ws + it.gram_off;
+    double* o = out + out_off[it.item];
+    for (int64_t e = threadIdx.x; e < (int64_t)n * n; e += blockDim.x) {
+        const int i = (int)(e / n), j = (int)(e % n);
+        const int r = i > j ? i : j, c = i > j ? j : i;
+        o[e] = it.full ? G[(int64_t)r * n + c] : G[poff(r) + c];
+    }
+}
+
+int vsp_plan_debug_gram(vsp_plan* p, const void* const* d_ptrs, double* d_out, void* d_workspace,
+                        int64_t workspace_bytes, void* stream) {
+    if (!p || !d_ptrs || !d_out || !d_workspace) return VSP_E_ARG;
+    if (p->count == 0) return VSP_OK;
+    uintptr_t base = reinterpret_cast<uintptr_t>(d_workspace);
+    uintptr_t aligned = (base + 255) & ~uintptr_t(255);
+    if ((int64_t)(aligned - base) + plan_f64_bytes(p) + p->i8_bytes > workspace_bytes) return VSP_E_WORKSPACE;
+    double* ws = reinterpret_cast<double*>(aligned);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    for (int s = 0; s < p->count; ++s) p->items[s].ptr = d_ptrs[p->order[s]];
+    VSP_CUDA(cudaMemcpyAsync(p->d_items, p->items.data(), sizeof(ItemDesc) * (size_t)p->count,
+                             cudaMemcpyHostToDevice, st));
+    for (const ShapeClass& c : p->classes) {
+        int rc;
+        if (p->dtype == VSP_F32 && p->gram_method == 1)
+            rc = launch_gram_i8(p, c, ws, reinterpret_cast<unsigned char*>(ws) + plan_f64_bytes(p), st);
+        else
+            rc = (p->dtype == VSP_F32) ? launch_gram<float>(p, c, ws, st) : launch_gram<double>(p, c, ws, st);
+        if (rc != VSP_OK) return rc;
+    }
+    std::vector<int64_t> off(p->count + 1, 0);  // caller order
+    {
+        std::vector<int> nn(p->count);
+        for (int s = 0; s < p->count; ++s) nn[p->items[s].item] = p->items[s].n;
+        for (int i = 0; i < p->count; ++i) off[i + 1] = off[i] + (int64_t)nn[i] * nn[i];
+    }
+    int64_t* d_off = nullptr;
+    VSP_CUDA(cudaMalloc(&d_off, sizeof(int64_t) * (size_t)p->count));
+    VSP_CUDA(cudaMemcpyAsync(d_off, off.data(), sizeof(int64_t) * (size_t)p->count, cudaMemcpyHostToDevice, st));
+    expand_gram_kernel<<<p->count, 256, 0, st>>>(p->d_items, ws, d_off, d_out);
+    VSP_CUDA(cudaGetLastError());
+    VSP_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_off);
     return VSP_OK;
 }
 

@@ -17,7 +17,8 @@
 //   slice_i8_kernel    fp32 W -> row exponents E[n] and six int8 digit planes S_t[n][Kp],
 //                      K-major, K padded to a multiple of 64 with zeros (also transposes the
 //                      tall case, so the MMA kernel only ever sees K-major operands).
-//   gram_i8_mma_kernel one CTA per 128x64 output tile of the lower triangle:
+//   gram_i8_mma_kernel one CTA per 128-row block of one matrix, looping over its 64-column
+//                      tiles of the lower triangle (TMEM, barriers and the pipeline are set up once):
 //        warp 0    TMA producer: 12 boxes per 64-byte K chunk (6 A planes 128x64B, 6 B planes
 //                  64x64B, SWIZZLE_64B) into a 3-stage shared-memory ring (mbarrier full/empty)
 //        warp 1    allocates 512 TMEM columns, one elected lane issues 26 pairs x 2
@@ -50,8 +51,8 @@ struct I8Class {
     int begin, count;   // item range in the plan's sorted item table (sorted by n, then kp)
     int64_t slice_off;  // byte offset of the [count][6][n][kp] digit planes in the workspace
     int64_t exp_off;    // byte offset of the [count][n] int32 row exponents
-    int ntiles;
-    unsigned char tile_m[kI8MaxTiles], tile_n[kI8MaxTiles];  // lower-triangle 128x64 tiles
+    int mtiles;                          // 128-row tiles
+    unsigned char nt_count[kI8MaxTiles];  // 64-column tiles of the lower triangle per 128-row tile
 };
 
 // ---------------------------------------------------------------------------------- slicing
@@ -115,11 +116,19 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) e = max(e, __shfl_xor_sync(0xffffffffu, e, o));
             if (lane == 0) Eout[i] = e;
-            for (int k = lane; k < kp; k += 32) {
-                signed char dg[kDigits] = {0, 0, 0, 0, 0, 0};
-                if (k < K) f32_digits(__float_as_uint(row[k]), e, dg);
+            // four consecutive k per lane: one 32-bit store per digit plane
+            for (int k = 4 * lane; k < kp; k += 128) {
+                unsigned pk[kDigits] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
-                for (int t = 0; t < kDigits; ++t) planes[((int64_t)t * n + i) * kp + k] = dg[t];
+                for (int u = 0; u < 4; ++u) {
+                    signed char dg[kDigits] = {0, 0, 0, 0, 0, 0};
+                    if (k + u < K) f32_digits(__float_as_uint(row[k + u]), e, dg);
+#pragma unroll
+                    for (int t = 0; t < kDigits; ++t) pk[t] |= (unsigned)(unsigned char)dg[t] << (8 * u);
+                }
+#pragma unroll
+                for (int t = 0; t < kDigits; ++t)
+                    *reinterpret_cast<unsigned*>(planes + ((int64_t)t * n + i) * kp + k) = pk[t];
             }
         }
     } else {
@@ -226,16 +235,19 @@ __global__ void __launch_bounds__(192, 1)
                        const __grid_constant__ CUtensorMap tmB) {
     extern __shared__ unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const ItemDesc it = items[cls.begin + blockIdx.x];
+    const int item = blockIdx.y;  // tiles of one matrix are adjacent in launch order: they share L2
+    const int mt = blockIdx.x;
+    const ItemDesc it = items[cls.begin + item];
     const int n = it.n;
-    const int mt = cls.tile_m[blockIdx.y], nt = cls.tile_n[blockIdx.y];
+    const int ntiles = cls.nt_count[mt];
     const int nchunks = cls.kp / kI8ChunkK;
 
     unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(tiles + kI8Stages * kI8StageBytes);
-    // bars[0..2] full, bars[3..5] empty, bars[6] accumulators ready; then the TMEM base address
+    // bars[0..2] full, [3..5] empty, [6] accumulators ready, [7] accumulators drained; then the TMEM base
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 8);
-    const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + kI8Stages), accbar = smem_u32(bars + 2 * kI8Stages);
+    const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + kI8Stages);
+    const unsigned accbar = smem_u32(bars + 2 * kI8Stages), drainbar = smem_u32(bars + 2 * kI8Stages + 1);
 
     if (tid == 0) {
         for (int s = 0; s < kI8Stages; ++s) {
@@ -243,6 +255,7 @@ __global__ void __launch_bounds__(192, 1)
             mbar_init(empty0 + 8 * s, 1);
         }
         mbar_init(accbar, 1);
+        mbar_init(drainbar, 4);  // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // whole warp: allocate all 512 TMEM columns (7 levels x 64 used)
@@ -257,18 +270,21 @@ __global__ void __launch_bounds__(192, 1)
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            const int rowA = blockIdx.x * kDigits * n + mt * kI8TileM;  // + t*n per digit plane
-            const int rowB = blockIdx.x * kDigits * n + nt * kI8TileN;
-            for (int c = 0; c < nchunks; ++c) {
-                const int s = c % kI8Stages;
-                if (c >= kI8Stages) mbar_wait(empty0 + 8 * s, ((c / kI8Stages) - 1) & 1);
-                mbar_expect_tx(full0 + 8 * s, kI8StageBytes);
-                const unsigned base = smem_u32(tiles + s * kI8StageBytes);
+            const int rowA = item * kDigits * n + mt * kI8TileM;  // + t*n per digit plane
+            int g = 0;                                            // chunk counter over all tiles
+            for (int nt = 0; nt < ntiles; ++nt) {
+                const int rowB = item * kDigits * n + nt * kI8TileN;
+                for (int c = 0; c < nchunks; ++c, ++g) {
+                    const int s = g % kI8Stages;
+                    if (g >= kI8Stages) mbar_wait(empty0 + 8 * s, ((g / kI8Stages) - 1) & 1);
+                    mbar_expect_tx(full0 + 8 * s, kI8StageBytes);
+                    const unsigned base = smem_u32(tiles + s * kI8StageBytes);
 #pragma unroll
-                for (int t = 0; t < kDigits; ++t) {
-                    tma_load_2d(base + t * (kI8TileM * kI8ChunkK), &tmA, full0 + 8 * s, c * kI8ChunkK, rowA + t * n);
-                    tma_load_2d(base + kDigits * kI8TileM * kI8ChunkK + t * (kI8TileN * kI8ChunkK), &tmB,
-                                full0 + 8 * s, c * kI8ChunkK, rowB + t * n);
+                    for (int t = 0; t < kDigits; ++t) {
+                        tma_load_2d(base + t * (kI8TileM * kI8ChunkK), &tmA, full0 + 8 * s, c * kI8ChunkK, rowA + t * n);
+                        tma_load_2d(base + kDigits * kI8TileM * kI8ChunkK + t * (kI8TileN * kI8ChunkK), &tmB,
+                                    full0 + 8 * s, c * kI8ChunkK, rowB + t * n);
+                    }
                 }
             }
         }
@@ -278,74 +294,116 @@ __global__ void __launch_bounds__(192, 1)
             // instruction descriptor: D = S32, A = B = signed int8, both K-major, N = 64, M = 128
             const unsigned idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(kI8TileN >> 3) << 17) |
                                    ((unsigned)(kI8TileM >> 4) << 24);
-            for (int c = 0; c < nchunks; ++c) {
-                const int s = c % kI8Stages;
-                mbar_wait(full0 + 8 * s, (c / kI8Stages) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const unsigned baseA = smem_u32(tiles + s * kI8StageBytes);
-                const unsigned baseB = baseA + kDigits * kI8TileM * kI8ChunkK;
+            const unsigned long long adesc0 = umma_desc_sw64(smem_u32(tiles));
+            const unsigned long long bdesc0 = umma_desc_sw64(smem_u32(tiles) + kDigits * kI8TileM * kI8ChunkK);
+            int g = 0;
+            for (int ti = 0; ti < ntiles; ++ti) {
+                if (ti > 0) {  // the epilogue must have drained the accumulators of the previous tile
+                    mbar_wait(drainbar, (ti - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                for (int c = 0; c < nchunks; ++c, ++g) {
+                    const int s = g % kI8Stages;
+                    mbar_wait(full0 + 8 * s, (g / kI8Stages) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    // descriptors differ from the stage-0 ones only in the 16-byte-granular start
+                    // address field: one 64-bit add per operand instead of rebuilding them
+                    const unsigned long long adS = adesc0 + (unsigned long long)(s * (kI8StageBytes >> 4));
+                    const unsigned long long bdS = bdesc0 + (unsigned long long)(s * (kI8StageBytes >> 4));
 #pragma unroll
-                for (int lv = 0; lv < kLevels; ++lv) {
-                    const int tlo = lv > kDigits - 1 ? lv - (kDigits - 1) : 0;
-                    const int thi = lv < kDigits - 1 ? lv : kDigits - 1;
-                    for (int t = tlo; t <= thi; ++t) {
-                        const unsigned long long ad = umma_desc_sw64(baseA + t * (kI8TileM * kI8ChunkK));
-                        const unsigned long long bd = umma_desc_sw64(baseB + (lv - t) * (kI8TileN * kI8ChunkK));
+                    for (int lv = 0; lv < kLevels; ++lv) {
+                        constexpr int kTop = kDigits - 1;
+                        const int tlo = lv > kTop ? lv - kTop : 0;
+                        const int thi = lv < kTop ? lv : kTop;
 #pragma unroll
-                        for (int ks = 0; ks < kI8ChunkK / 32; ++ks) {
-                            const unsigned acc = (c > 0 || t > tlo || ks > 0) ? 1u : 0u;
-                            umma_i8(tmem_base + lv * kI8TileN, ad + 2 * ks, bd + 2 * ks, idesc, acc);
+                        for (int t = 0; t < kDigits; ++t) {
+                            if (t < tlo || t > thi) continue;
+#pragma unroll
+                            for (int ks = 0; ks < kI8ChunkK / 32; ++ks) {
+                                const unsigned acc = (c > 0 || t > tlo || ks > 0) ? 1u : 0u;
+                                umma_i8(tmem_base + lv * kI8TileN,
+                                        adS + (unsigned long long)(((t * kI8TileM * kI8ChunkK) >> 4) + 2 * ks),
+                                        bdS + (unsigned long long)((((lv - t) * kI8TileN * kI8ChunkK) >> 4) + 2 * ks),
+                                        idesc, acc);
+                            }
                         }
                     }
+                    umma_commit(empty0 + 8 * s);  // the stage is free once these MMAs have read it
                 }
-                umma_commit(empty0 + 8 * s);  // the stage is free once these MMAs have read it
+                umma_commit(accbar);
             }
-            umma_commit(accbar);
         }
     } else {
         // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
         const int q = warp & 3;
         const int i = mt * kI8TileM + 32 * q + lane;  // Gram row of this thread
-        const int* __restrict__ E = reinterpret_cast<const int*>(wsb + cls.exp_off) + (int64_t)blockIdx.x * n;
+        const int* __restrict__ E = reinterpret_cast<const int*>(wsb + cls.exp_off) + (int64_t)item * n;
         const int Ei = (i < n) ? E[i] : 1;
         double* __restrict__ G = ws + it.gram_off;
-        mbar_wait(accbar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int ti = 0; ti < ntiles; ++ti) {
+            const int nt = ti;
+            mbar_wait(accbar, ti & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-        for (int cc = 0; cc < kI8TileN / 16; ++cc) {
-            double acc[16];
-            int r[16];
-            const unsigned taddr = tmem_base + ((unsigned)(32 * q) << 16) + cc * 16;
-            tmem_ld16(taddr, r);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int k = 0; k < 16; ++k) acc[k] = (double)r[k];
-#pragma unroll
-            for (int lv = 1; lv < kLevels; ++lv) {
-                tmem_ld16(taddr + lv * kI8TileN, r);
+            for (int cc = 0; cc < kI8TileN / 16; ++cc) {
+                // Horner over the levels in exact 64-bit integers, split in two so nothing overflows:
+                //   hi = P0 128^2 + P1 128 + P2 (< 2^42),  lo = P3 128^3 + ... + P6 (< 2^49),
+                //   sum_s P_s 128^(6-s) = hi 2^28 + lo   -> two conversions and one FMA per element
+                double acc[16];
+                long long hi[16];
+                int r[16];
+                const unsigned taddr = tmem_base + ((unsigned)(32 * q) << 16) + cc * 16;
+                tmem_ld16(taddr, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int k = 0; k < 16; ++k) acc[k] = fma(acc[k], 128.0, (double)r[k]);
-            }
-            if (i < n) {
+                for (int k = 0; k < 16; ++k) hi[k] = r[k];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const int j = nt * kI8TileN + cc * 16 + k;
-                    if (j <= i) {
-                        const int Ej = E[j];
-                        double g;
-                        if (Ei == 255 || Ej == 255) {
-                            g = __longlong_as_double(0x7ff8000000000000LL);  // NaN/Inf in the input row
-                        } else {
-                            // sum_k q_i q_j = 128^4 * acc ; x = q 2^(E-167)  ->  2^(Ei+Ej-334+28)
-                            const int be = Ei + Ej - 306 + 1023;
-                            g = acc[k] * __hiloint2double(be << 20, 0);
-                        }
-                        if (it.full) {
-                            G[(int64_t)i * n + j] = g;
-                            G[(int64_t)j * n + i] = g;
-                        } else {
-                            G[poff(i) + j] = g;
+                for (int lv = 1; lv < 3; ++lv) {
+                    tmem_ld16(taddr + lv * kI8TileN, r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) hi[k] = hi[k] * 128 + r[k];
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) acc[k] = (double)hi[k] * 268435456.0;  // 2^28
+                tmem_ld16(taddr + 3 * kI8TileN, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int k = 0; k < 16; ++k) hi[k] = r[k];
+#pragma unroll
+                for (int lv = 4; lv < kLevels; ++lv) {
+                    tmem_ld16(taddr + lv * kI8TileN, r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) hi[k] = hi[k] * 128 + r[k];
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) acc[k] += (double)hi[k];
+                if (cc == kI8TileN / 16 - 1) {  // every level of this tile has been read: release TMEM
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(drainbar) : "memory");
+                }
+                if (i < n) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const int j = nt * kI8TileN + cc * 16 + k;
+                        if (j <= i) {
+                            const int Ej = E[j];
+                            double g;
+                            if (Ei == 255 || Ej == 255) {
+                                g = __longlong_as_double(0x7ff8000000000000LL);  // NaN/Inf in the input row
+                            } else {
+                                // sum_k q_i q_j = 128^4 * acc ; x = q 2^(E-167)  ->  2^(Ei+Ej-334+28)
+                                const int be = Ei + Ej - 306 + 1023;
+                                g = acc[k] * __hiloint2double(be << 20, 0);
+                            }
+                            if (it.full) {
+                                G[(int64_t)i * n + j] = g;
+                                G[(int64_t)j * n + i] = g;
+                            } else {
+                                G[poff(i) + j] = g;
+                            }
                         }
                     }
                 }

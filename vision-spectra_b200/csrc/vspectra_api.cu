@@ -131,7 +131,7 @@ int launch_gram_i8(const vsp_plan* p, const ShapeClass& c, double* ws, unsigned 
         if (!cuda_ok(cudaFuncSetAttribute(gram_i8_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kI8SmemBytes),
                      "cudaFuncSetAttribute(gram_i8_mma_kernel)"))
             return VSP_E_CUDA;
-        dim3 mgrid(g.count, g.ntiles);
+        dim3 mgrid(g.mtiles, g.count);
         gram_i8_mma_kernel<<<mgrid, 192, kI8SmemBytes, st>>>(p->d_items, g, wsb, ws, tmA, tmB);
         g_launches++;
         if (!cuda_ok(cudaGetLastError(), "gram_i8_mma_kernel")) return VSP_E_CUDA;
@@ -286,14 +286,11 @@ int vsp_plan_create(int32_t count, const int32_t* rows, const int32_t* cols, con
                 c.kp = kp;
                 c.begin = s;
                 c.count = 0;
-                c.ntiles = 0;
-                for (int mt = 0; mt * kI8TileM < it.n; ++mt)
-                    for (int nt = 0; nt * kI8TileN < it.n && nt * kI8TileN <= mt * kI8TileM + kI8TileM - 1; ++nt)
-                        if (c.ntiles < kI8MaxTiles) {
-                            c.tile_m[c.ntiles] = (unsigned char)mt;
-                            c.tile_n[c.ntiles] = (unsigned char)nt;
-                            c.ntiles++;
-                        }
+                c.mtiles = (it.n + kI8TileM - 1) / kI8TileM;  // <= 32 for n <= VSP_MAX_N
+                for (int mt = 0; mt < c.mtiles; ++mt) {
+                    const int last_col = std::min(it.n - 1, mt * kI8TileM + kI8TileM - 1);
+                    c.nt_count[mt] = (unsigned char)(last_col / kI8TileN + 1);
+                }
                 p->i8classes.push_back(c);
             }
             p->i8classes.back().count++;

@@ -309,7 +309,9 @@ def run_b200_arm(args) -> None:
 
     # sanity: every record of the last step is a finished, finite analysis
     rec = res.records_host()
-    assert rec.shape[0] == matrices and int((rec["status"] != 0).sum()) == 0, "bench records not clean"
+    # status 0, or 96 = ill-conditioned (kappa > 3e4) and re-solved from W; nothing else is acceptable
+    assert rec.shape[0] == matrices and bool(((rec["status"] == 0) | (rec["status"] == 96)).all()), "bench records not clean"
+    n_refined = int((rec["status"] == 96).sum())
     if rank == 0 and world > 1:
         assert gathered.numel() == world * matrices * 64
 
@@ -338,7 +340,7 @@ def run_b200_arm(args) -> None:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * matrices * e2e_steps / float(e2e_s.item())
     d2h_bytes = rec_h.nbytes + (sv_h.nbytes if sv_h is not None else 0)
-    assert int((rec_h["status"] != 0).sum()) == 0
+    assert bool(((rec_h["status"] == 0) | (rec_h["status"] == 96)).all())
     np.testing.assert_allclose(rec_h["metrics"], rec["metrics"], rtol=1e-12)  # same answers both ways
 
     if rank != 0:
@@ -420,6 +422,7 @@ def run_b200_arm(args) -> None:
             "l2": "inputs (987 MB per GPU) larger than L2 (126 MB); no flush needed",
             "parallelism": f"independent checkpoints per rank x{world}; one NCCL gather of 64-byte records per step",
             "outputs": "singular values (f64) + 64-byte record per matrix",
+            "refined_per_gpu_per_step": n_refined,
         },
         "e2e": {"value": e2e_value, "unit": "matrices/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": int(d2h_bytes),
                 "steps": e2e_steps, "api": "vision_spectra_b200.sweep.SweepRunner.run_host (pinned host arenas)"},

@@ -64,7 +64,8 @@ extern "C" {
 #define VSP_ST_FEW_SV 4    /* fewer than 8 positive SVs -> alpha and Hill NaN         */
 #define VSP_ST_ALPHA_NAN 8 /* OLS window rejected (fit_range) or slope not finite     */
 #define VSP_ST_HILL_NAN 16 /* Hill mean-log <= 0 or not finite                        */
-#define VSP_ST_REFINED 32  /* small singular values re-solved by one-sided Jacobi     */
+#define VSP_ST_REFINED 32  /* singular values re-solved from W itself (FP64 bidiagonalisation) */
+#define VSP_ST_ILLCOND 64  /* Gram route saw lambda_min/lambda_max < 1e-9 (kappa > ~3e4)  */
 
 /* Options; every field -1 selects the reference's default. */
 typedef struct vsp_opts {

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../vision-spectra_b200/csrc/bisect_metrics.cuh"
+#include "../../vision-spectra_b200/csrc/refine_bidiag.cuh"
 #include "../../vision-spectra_b200/csrc/tridiag.cuh"
 
 using namespace vsp;
@@ -53,5 +54,34 @@ extern "C" int vsp_emul_eig_metrics(const double* gram, int n, int use_full, int
     ints6[3] = out.k;
     ints6[4] = out.status;
     ints6[5] = iters;
+    return 0;
+}
+
+// W: row-major rows x cols (f64).  Bidiagonalise the K x n column-major copy (Gram index on the
+// columns) and return the singular values (descending) and the metrics computed from them.
+extern "C" int vsp_emul_refine(const double* w, int rows, int cols, double* sv, double* metrics4, int* ints6) {
+    HostCtx ctx;
+    const int n = rows < cols ? rows : cols, K = rows < cols ? cols : rows;
+    std::vector<double> X((size_t)K * n);
+    double mx = 0.0;
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) mx = std::fmax(mx, std::fabs(w[(size_t)r * cols + c]));
+    int ex = 0;
+    if (mx > 0.0) (void)std::frexp(mx, &ex);
+    const double sc = std::ldexp(1.0, -ex);
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) {
+            const double x = w[(size_t)r * cols + c] * sc;
+            if (rows <= cols) X[(size_t)r * K + c] = x;   // column r of X = row r of W
+            else X[(size_t)c * K + r] = x;                // column c of X = column c of W
+        }
+    std::vector<double> dq(n), eq(n), u(n), lam(n), part(4);
+    std::vector<DE> de(2 * n);
+    bidiagonalize(ctx, X.data(), K, n, dq.data(), eq.data(), u.data(), part.data());
+    const int iters = gk_singular_values(ctx, dq.data(), eq.data(), n, de.data(), lam.data());
+    // scale of the Gram-route convention: lam are eigenvalues of (sc W)^T (sc W) -> scale = sc^2
+    MetricOut out = spectral_metrics(ctx, lam.data(), n, sc * sc, 0, -1, -1, -1, sv);
+    for (int q = 0; q < 4; ++q) metrics4[q] = out.metrics[q];
+    ints6[0] = out.m; ints6[1] = out.start; ints6[2] = out.end; ints6[3] = out.k; ints6[4] = out.status; ints6[5] = iters;
     return 0;
 }

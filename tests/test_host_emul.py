@@ -78,3 +78,21 @@ def test_emulated_optional_arguments(emul):
     assert metric_close(float(met[3]), g["hill_k7"]) and ints[3] == 7
     _, met, _ = run(emul, w, fs=5, fe=4000)
     assert np.isnan(met[2])
+
+
+@pytest.mark.parametrize("name", ["illcond:50", "powerlaw:100:4.0:f64", "powerlaw:100:2.0:f64", "rank1:10", "vit:C:0:v",
+                                  "randn:257x65:f32", "randn:9x33:f32", "randn:100x4:f32", "randn:1x1:f32", "eye:10", "sgd:96x384"])
+def test_emulated_refine_path(emul, name):
+    """The re-solve of ill-conditioned matrices (refine_bidiag.cuh: FP64 bidiagonalisation of W +
+    bisection on the Golub-Kahan form) holds the element-wise 1e-5 gate where the Gram route cannot."""
+    w = np.ascontiguousarray(np.asarray(build_case(name), np.float64))
+    n = min(w.shape)
+    sv, met, ints = np.zeros(n), np.zeros(4), np.zeros(6, np.int32)
+    emul.vsp_emul_refine(w.ctypes.data_as(ctypes.c_void_p), w.shape[0], w.shape[1], sv.ctypes.data_as(ctypes.c_void_p),
+                         met.ctypes.data_as(ctypes.c_void_p), ints.ctypes.data_as(ctypes.c_void_p))
+    g = RECORDS[name]
+    nrm, elem = sv_errors(sv, SVS[name])
+    assert elem < 1e-5 and nrm < 1e-12, (elem, nrm)
+    for q, k in enumerate(KEYS):
+        assert metric_close(float(met[q]), g["metrics"][k]), (k, met[q], g["metrics"][k])
+    assert ints[:4].tolist() == [g["ints"]["m"], g["ints"]["start"], g["ints"]["end"], g["ints"]["k"]]

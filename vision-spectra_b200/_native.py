@@ -15,7 +15,7 @@ import numpy as np
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libvspectra.so"
 
 VSP_F32, VSP_F64 = 0, 1
-ST_NONFINITE, ST_ZERO, ST_FEW_SV, ST_ALPHA_NAN, ST_HILL_NAN, ST_REFINED = 1, 2, 4, 8, 16, 32
+ST_NONFINITE, ST_ZERO, ST_FEW_SV, ST_ALPHA_NAN, ST_HILL_NAN, ST_REFINED, ST_ILLCOND = 1, 2, 4, 8, 16, 32, 64
 
 # vsp_record, 64 bytes
 RECORD_DTYPE = np.dtype(

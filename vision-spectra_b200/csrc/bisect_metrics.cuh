@@ -184,6 +184,37 @@ VSP_DEV int bisect_all(Ctx& ctx, const DE* de, int n, const TriInfo& t, double* 
     return maxit;
 }
 
+// Gram route: lambda_min <= ratio * lambda_max (kappa >~ 3e4) marks the matrix for the re-solve
+// from W itself (refine_bidiag.cuh); below that ratio eps * kappa^2 eats into the 1e-5 gate.
+constexpr double kRefineRatio = 1e-9;
+
+// Early test used by the tridiagonalisation kernels (one thread): is there an eigenvalue of
+// T (d, e) below kRefineRatio times the Gershgorin upper bound?  Same product-form recurrence
+// and e^2 floor as sturm_count2.
+VSP_DEV bool has_tiny_eigenvalue(const double* d, const double* e, int n) {
+    double gu = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double el = (i > 0) ? fabs(e[i - 1]) : 0.0, er = (i < n - 1) ? fabs(e[i]) : 0.0;
+        gu = fmax(gu, d[i] + el + er);
+    }
+    const double x = kRefineRatio * gu;
+    double p0 = 1.0, p1 = d[0] - x;
+    int changes = (p1 < 0.0) ? 1 : 0;
+    for (int i = 1; i < n && changes == 0; ++i) {
+        const double e2 = fmax(e[i - 1] * e[i - 1], kE2Floor);
+        const double p2 = (d[i] - x) * p1 - e2 * p0;
+        if ((p2 < 0.0) != (p1 < 0.0)) changes = 1;
+        p0 = p1;
+        p1 = p2;
+        if ((i & 7) == 7) {
+            const double s = rescale_factor(p0, p1);
+            p0 *= s;
+            p1 *= s;
+        }
+    }
+    return changes != 0;
+}
+
 struct MetricOut {
     double metrics[4];
     int m, start, end, k, status;
@@ -217,6 +248,7 @@ VSP_DEV MetricOut spectral_metrics(Ctx& ctx, double* lam, int n, double scale, i
     // <= 0.  LAPACK on W itself reports them as tiny positive numbers, so
     // floor at (eps * sigma_max)^2 instead of dropping them: m stays min(rows, cols).
     const double lfloor = lmax * 4.930380657631324e-32;  // 2^-104
+    if (lam[0] <= kRefineRatio * lmax) out.status |= VSP_ST_ILLCOND;
     ctx.sync();
     for (int i = ctx.tid; i < n; i += ctx.nthreads)
         if (!(lam[i] > lfloor)) lam[i] = lfloor;

@@ -43,7 +43,15 @@ struct ItemDesc {
 VSP_HD int64_t tri(int64_t i) { return (i * (i + 1)) >> 1; }
 
 // misc[] slots written by the tridiagonalisation stage
-enum { MISC_SCALE = 0, MISC_FLAGS = 1, MISC_UNUSED0 = 2, MISC_UNUSED1 = 3, MISC_COUNT = 4 };
+enum { MISC_SCALE = 0, MISC_FLAGS = 1, MISC_SLOT = 2, MISC_UNUSED1 = 3, MISC_COUNT = 4 };
+
+// Claim ticket for the ill-conditioned re-solve: the tridiagonalisation kernels test the small
+// end of the spectrum with one Sturm count and, if it is populated, take a slot of the FP64 pool.
+struct RefineGate {
+    int* counter;     // zeroed by the host before every execution; nullptr = re-solve disabled
+    int* slot_items;  // slot -> position of the claiming item in the plan's item table
+    int slots;
+};
 
 #if !defined(__CUDACC__)
 // ----------------------------------------------------------------- host emulation
@@ -60,6 +68,8 @@ using std::sqrt;
 struct HostCtx {
     int tid = 0;
     int nthreads = 1;
+    int lane = 0, warp = 0, nwarps = 1, wsize = 1;  // a "warp" of one lane
+    double warp_sum(double v) { return v; }
     void sync() {}
     double sum(double v) { return v; }
     double max(double v) { return v; }
@@ -76,10 +86,18 @@ struct HostCtx {
 struct CtaCtx {
     int tid;
     int nthreads;
+    int lane, warp, nwarps, wsize;
     double* red;  // shared scratch: 2 rows x 32 warps x 4 values
     int flip;
 
-    __device__ CtaCtx(double* scratch) : tid(threadIdx.x), nthreads(blockDim.x), red(scratch), flip(0) {}
+    __device__ CtaCtx(double* scratch)
+        : tid(threadIdx.x), nthreads(blockDim.x), lane(threadIdx.x & 31), warp(threadIdx.x >> 5),
+          nwarps(blockDim.x >> 5), wsize(32), red(scratch), flip(0) {}
+    __device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
     static constexpr int kScratchDoubles = 2 * 32 * 4;
 
     __device__ __forceinline__ void sync() { __syncthreads(); }
@@ -93,8 +111,25 @@ struct CtaCtx {
         const int nw = (nthreads + 31) >> 5;
         if ((tid & 31) == 0) row[tid >> 5] = v;
         __syncthreads();
-        double r = row[0];
-        for (int w = 1; w < nw; ++w) r = op(r, row[w]);
+        if (nw <= 8) {
+            double r = row[0];
+            for (int w = 1; w < nw; ++w) r = op(r, row[w]);
+            return r;
+        }
+        // many warps: one partial per lane and a second (masked) butterfly instead of nw serial loads
+        bool have = lane < nw;
+        double r = have ? row[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double other = __shfl_xor_sync(0xffffffffu, r, o);
+            const bool ohave = __shfl_xor_sync(0xffffffffu, (int)have, o) != 0;
+            if (have && ohave)
+                r = op(r, other);
+            else if (ohave) {
+                r = other;
+                have = true;
+            }
+        }
         return r;
     }
     __device__ __forceinline__ double sum(double v) {

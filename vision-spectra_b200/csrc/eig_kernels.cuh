@@ -9,6 +9,7 @@
 #pragma once
 
 #include "bisect_metrics.cuh"
+#include "refine_bidiag.cuh"
 #include "tridiag.cuh"
 #include "tridiag_fused.cuh"
 
@@ -28,7 +29,7 @@ __host__ __device__ inline int bisect_threads(int n) {  // two eigenvalues per t
 }
 
 __global__ void tridiag_global_kernel(const ItemDesc* __restrict__ items, int item_base, double* __restrict__ ws,
-                                      int npad) {
+                                      int npad, RefineGate gate) {
     extern __shared__ __align__(16) double smem[];
     const ItemDesc it = items[item_base + blockIdx.x];
     const int n = it.n;
@@ -69,8 +70,17 @@ __global__ void tridiag_global_kernel(const ItemDesc* __restrict__ items, int it
         out[n + i] = e[i];
     }
     if (ctx.tid == 0) {
+        int oflags = 0, slot = -1;
+        if (gate.counter != nullptr && has_tiny_eigenvalue(d, e, n)) {
+            slot = atomicAdd(gate.counter, 1);
+            if (slot < gate.slots) {
+                oflags = VSP_ST_ILLCOND;
+                gate.slot_items[slot] = item_base + blockIdx.x;
+            }
+        }
         out[2 * n + MISC_SCALE] = scale;
-        out[2 * n + MISC_FLAGS] = 0.0;
+        out[2 * n + MISC_FLAGS] = (double)oflags;
+        out[2 * n + MISC_SLOT] = (double)slot;
     }
 }
 
@@ -94,6 +104,7 @@ __global__ void bisect_metrics_kernel(const ItemDesc* __restrict__ items, int it
     }
     const double scale = in[2 * n + MISC_SCALE];
     const int flags = (int)in[2 * n + MISC_FLAGS];
+    if (flags & VSP_ST_ILLCOND) return;  // claimed by refine_kernel, which runs concurrently and writes the record
     ctx.sync();
     int iters = 0;
     if (!flags) {
@@ -114,6 +125,102 @@ __global__ void bisect_metrics_kernel(const ItemDesc* __restrict__ items, int it
         vsp_record r;
         r.item = it.item;
         r.status = mo.status;
+        r.m = mo.m;
+        r.start = mo.start;
+        r.end = mo.end;
+        r.k = mo.k;
+        r.n = n;
+        r.iters = iters;
+        r.metrics[0] = mo.metrics[0];
+        r.metrics[1] = mo.metrics[1];
+        r.metrics[2] = mo.metrics[2];
+        r.metrics[3] = mo.metrics[3];
+        records[it.item] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Re-solve of the matrices the tridiagonalisation flagged VSP_ST_ILLCOND (refine_bidiag.cuh).
+// One CTA per pool slot: CTA s serves the item that claimed slot s (slots are handed out in
+// increasing order, so the working CTAs are scheduled first and the rest exit at once).
+struct RefinePool {
+    double* base;        // slots x slot_doubles
+    int slots;
+    int64_t slot_doubles;
+};
+constexpr int kRefineMaxN = 2048;
+__host__ __device__ inline size_t refine_smem_fixed_bytes(int npad) {
+    return sizeof(double) * (8 * (size_t)npad + 1024 + CtaCtx::kScratchDoubles + 2);
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(1024)
+    refine_kernel(const ItemDesc* __restrict__ items, RefineGate gate, RefinePool pool, int npad, int xs_doubles,
+                  vsp_opts opts, double* __restrict__ sv_out, vsp_record* __restrict__ records) {
+    extern __shared__ __align__(16) double smem[];
+    const int slot = blockIdx.x;
+    if (slot >= *gate.counter) return;  // unclaimed slot
+    const ItemDesc it = items[gate.slot_items[slot]];
+    const int n = it.n, K = it.kdim;
+    double* red = smem;
+    double* dq = red + CtaCtx::kScratchDoubles;
+    double* eq = dq + npad;
+    double* u = eq + npad;
+    double* lam = u + npad;
+    double* part = lam + npad;                                  // [1024]
+    DE* de = reinterpret_cast<DE*>(part + 1024);                // [2 npad]
+    int* slot_s = reinterpret_cast<int*>(de + 2 * (size_t)npad);
+    CtaCtx ctx(red);
+    double* X = pool.base + (int64_t)slot * pool.slot_doubles;
+    const TIn* __restrict__ W = reinterpret_cast<const TIn*>(it.ptr);
+
+    // scale by a power of two so that max |x| is in [0.5, 1)
+    double mx = 0.0;
+    for (int64_t e = ctx.tid; e < (int64_t)it.rows * it.cols; e += ctx.nthreads) {
+        const int r = (int)(e / it.cols), c = (int)(e % it.cols);
+        mx = fmax(mx, fabs((double)W[(int64_t)r * it.ld + c]));
+    }
+    mx = ctx.max(mx);
+    int ex = 0;
+    (void)frexp(mx, &ex);
+    const double sc = ldexp(1.0, -ex);
+    // X: column-major K x n with the Gram index on the columns
+    if (!it.trans) {  // n = rows: column i of X is row i of W
+        for (int64_t e = ctx.tid; e < (int64_t)n * K; e += ctx.nthreads) {
+            const int i = (int)(e / K), k = (int)(e % K);
+            X[e] = (double)W[(int64_t)i * it.ld + k] * sc;
+        }
+    } else {  // n = cols: column i of X is column i of W
+        for (int64_t e = ctx.tid; e < (int64_t)n * K; e += ctx.nthreads) {
+            const int k = (int)(e / n), i = (int)(e % n);  // read W coalesced
+            X[(int64_t)i * K + k] = (double)W[(int64_t)k * it.ld + i] * sc;
+        }
+    }
+    __threadfence_block();
+    ctx.sync();
+    // first steps on the global (L2) copy until the trailing block fits in shared memory
+    double* Xs = reinterpret_cast<double*>(slot_s + 2);
+    int j0 = 0;
+    while (j0 < n && (int64_t)(K - j0) * (n - j0) > (int64_t)xs_doubles) ++j0;
+    if (j0 > 0) bidiag_steps(ctx, X, K, K, n, 0, j0, dq, eq, u, part);
+    if (j0 < n) {
+        const int lds = K - j0, nc = n - j0;
+        for (int64_t e = ctx.tid; e < (int64_t)lds * nc; e += ctx.nthreads) {
+            const int c = (int)(e / lds), r = (int)(e % lds);
+            Xs[e] = X[(int64_t)(c + j0) * K + (r + j0)];
+        }
+        ctx.sync();
+        // same indexing X[c*ld + r] with c, r >= j0 on the shifted base
+        bidiag_steps(ctx, Xs - ((int64_t)j0 * lds + j0), lds, K, n, j0, n, dq, eq, u, part);
+    }
+    int iters = gk_singular_values(ctx, dq, eq, n, de, lam);
+    iters = ctx.max_i(iters);  // barrier: lam[] complete
+    double* sv = (opts.want_sv != 0 && sv_out != nullptr) ? sv_out + it.sv_off : nullptr;
+    const MetricOut mo = spectral_metrics(ctx, lam, n, sc * sc, 0, opts.fit_start, opts.fit_end, opts.hill_k, sv);
+    if (ctx.tid == 0) {
+        vsp_record r;
+        r.item = it.item;
+        r.status = mo.status | VSP_ST_ILLCOND | VSP_ST_REFINED;
         r.m = mo.m;
         r.start = mo.start;
         r.end = mo.end;

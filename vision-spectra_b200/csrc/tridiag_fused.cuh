@@ -32,6 +32,7 @@
 
 #include <cstdio>
 
+#include "bisect_metrics.cuh"
 #include "common.cuh"
 
 namespace vsp {
@@ -201,7 +202,7 @@ __device__ __forceinline__ void pair_dispatch(double* __restrict__ row0, int r0,
 template <int NP>
 __global__ void __launch_bounds__(256, 2)
     tridiag_fused_kernel(const ItemDesc* __restrict__ items, int item_base, double* __restrict__ ws, int npad,
-                         int rows_smem, int debug_timing) {
+                         int rows_smem, int debug_timing, RefineGate gate) {
     extern __shared__ __align__(16) double smem[];
     const ItemDesc it = items[item_base + blockIdx.x];
     const int n = it.n;
@@ -461,8 +462,17 @@ __global__ void __launch_bounds__(256, 2)
         out[n + i] = e[i];
     }
     if (tid == 0) {
+        int oflags = 0, slot = -1;
+        if (gate.counter != nullptr && has_tiny_eigenvalue(d, e, n)) {  // kappa >~ 3e4: re-solve from W
+            slot = atomicAdd(gate.counter, 1);
+            if (slot < gate.slots) {
+                oflags = VSP_ST_ILLCOND;
+                gate.slot_items[slot] = item_base + blockIdx.x;
+            }
+        }
         out[2 * n + MISC_SCALE] = scale;
-        out[2 * n + MISC_FLAGS] = 0.0;
+        out[2 * n + MISC_FLAGS] = (double)oflags;
+        out[2 * n + MISC_SLOT] = (double)slot;
     }
 }
 

@@ -46,6 +46,11 @@ struct ShapeClass {
     int begin;   // first item (sorted order)
     int count;
     int npad, split;
+    int refine_slots;             // FP64 pool of the ill-conditioned re-solve
+    int64_t refine_slot_doubles;  // max K*n over the class
+    int64_t refine_off;           // byte offset of the pool in the refine region
+    int64_t refine_items_off;     // byte offset of the slot -> item table
+    int refine_counter;           // index of this class's slot counter
 };
 
 int validate(int32_t count, const int32_t* rows, const int32_t* cols, const int64_t* ld) {
@@ -70,11 +75,15 @@ struct vsp_plan {
     std::vector<ShapeClass> classes;
     std::vector<I8Class> i8classes;  // fp32 inputs: (n, Kp) groups sharing one digit-plane tensor
     int64_t i8_bytes = 0;            // digit planes + row exponents, after the FP64 region
+    int64_t refine_bytes = 0;        // slot counters (first 1 KB) + FP64 pools, after the int8 region
     int gram_method = 1;             // 1: tcgen05 int8 split (fp32 inputs), 0: FP64 CUDA cores
     int64_t ws_doubles = 0;
     int64_t sv_total = 0;
     ItemDesc* d_items = nullptr;
     int device = -1;
+    // the re-solve of ill-conditioned items runs beside the bisection kernel on a forked stream
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -205,7 +214,11 @@ int64_t vsp_workspace_bytes(int32_t count, const int32_t* rows, const int32_t* c
         i8 += round_up64((int64_t)kDigits * n * round_up(std::max(rows[i], cols[i]), kI8ChunkK), 1024) +
               round_up64((int64_t)n * 4, 1024);
     }
-    return round_up64(total * (int64_t)sizeof(double), 1024) + i8 + 2048;
+    // re-solve pools: at most one slot per item (plans use count/8 slots per shape class)
+    int64_t refine = 1024;
+    for (int i = 0; i < count; ++i)
+        refine += round_up64((int64_t)rows[i] * cols[i] * 8, 1024) + 1024;
+    return round_up64(total * (int64_t)sizeof(double), 1024) + i8 + refine + 2048;
 }
 
 int vsp_plan_create(int32_t count, const int32_t* rows, const int32_t* cols, const int64_t* ld, int32_t dtype,
@@ -303,10 +316,35 @@ int vsp_plan_create(int32_t count, const int32_t* rows, const int32_t* cols, con
         }
         p->i8_bytes = boff;
     }
+    if (const char* e = std::getenv("VSP_REFINE")) {  // experiments: VSP_REFINE=0 disables the re-solve
+        if (std::string(e) == "0") p->opts.refine = 0;
+    }
+    if (p->opts.refine != 0) {
+        int64_t roff = 1024;  // the slot counters live in the first KB
+        int idx = 0;
+        for (ShapeClass& c : p->classes) {
+            c.refine_slots = 0;
+            if (c.n > kRefineMaxN || idx >= 256) continue;
+            int64_t kn = 0;
+            for (int s = c.begin; s < c.begin + c.count; ++s)
+                kn = std::max<int64_t>(kn, (int64_t)p->items[s].kdim * p->items[s].n);
+            c.refine_slot_doubles = round_up64(kn, 4);
+            c.refine_slots = std::min(c.count, std::max(4, c.count / 8));
+            c.refine_counter = idx++;
+            c.refine_items_off = roff;  // slot -> item table
+            roff += round_up64((int64_t)c.refine_slots * 4, 1024);
+            c.refine_off = roff;
+            roff += round_up64(c.refine_slot_doubles * 8 * c.refine_slots, 1024);
+        }
+        p->refine_bytes = roff;
+    }
     if (count > 0) {
         if (!cuda_ok(cudaGetDevice(&p->device), "cudaGetDevice") ||
-            !cuda_ok(cudaMalloc(&p->d_items, sizeof(ItemDesc) * (size_t)count), "cudaMalloc(items)")) {
-            delete p;
+            !cuda_ok(cudaMalloc(&p->d_items, sizeof(ItemDesc) * (size_t)count), "cudaMalloc(items)") ||
+            !cuda_ok(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking), "cudaStreamCreate(side)") ||
+            !cuda_ok(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming), "cudaEventCreate") ||
+            !cuda_ok(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming), "cudaEventCreate")) {
+            vsp_plan_destroy(p);
             return VSP_E_CUDA;
         }
     }
@@ -317,13 +355,16 @@ int vsp_plan_create(int32_t count, const int32_t* rows, const int32_t* cols, con
 static int64_t plan_f64_bytes(const vsp_plan* plan) { return round_up64(plan->ws_doubles * (int64_t)sizeof(double), 1024); }
 
 int64_t vsp_plan_workspace_bytes(const vsp_plan* plan) {
-    return plan ? plan_f64_bytes(plan) + plan->i8_bytes + 2048 : VSP_E_ARG;
+    return plan ? plan_f64_bytes(plan) + plan->i8_bytes + plan->refine_bytes + 2048 : VSP_E_ARG;
 }
 int64_t vsp_plan_sv_count(const vsp_plan* plan) { return plan ? plan->sv_total : VSP_E_ARG; }
 
 void vsp_plan_destroy(vsp_plan* plan) {
     if (!plan) return;
     if (plan->d_items) cudaFree(plan->d_items);
+    if (plan->side) cudaStreamDestroy(plan->side);
+    if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
+    if (plan->ev_join) cudaEventDestroy(plan->ev_join);
     delete plan;
 }
 
@@ -336,9 +377,12 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
     // align the workspace to 256 bytes inside the caller's buffer
     uintptr_t base = reinterpret_cast<uintptr_t>(d_workspace);
     uintptr_t aligned = (base + 255) & ~uintptr_t(255);
-    if ((int64_t)(aligned - base) + plan_f64_bytes(p) + p->i8_bytes > workspace_bytes) return VSP_E_WORKSPACE;
+    if ((int64_t)(aligned - base) + plan_f64_bytes(p) + p->i8_bytes + p->refine_bytes > workspace_bytes)
+        return VSP_E_WORKSPACE;
     double* ws = reinterpret_cast<double*>(aligned);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned char* refine_base = reinterpret_cast<unsigned char*>(ws) + plan_f64_bytes(p) + p->i8_bytes;
+    if (p->refine_bytes > 0) VSP_CUDA(cudaMemsetAsync(refine_base, 0, 1024, st));  // slot counters
 
     for (int s = 0; s < p->count; ++s) {
         const void* ptr = d_ptrs[p->order[s]];
@@ -368,6 +412,12 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
             rc = (p->dtype == VSP_F32) ? launch_gram<float>(p, c, ws, st) : launch_gram<double>(p, c, ws, st);
         if (rc != VSP_OK) return rc;
         if ((rc = mark()) != VSP_OK) return rc;
+        RefineGate gate{nullptr, nullptr, 0};
+        if (c.refine_slots > 0) {
+            gate.counter = reinterpret_cast<int*>(refine_base) + c.refine_counter;
+            gate.slot_items = reinterpret_cast<int*>(refine_base + c.refine_items_off);
+            gate.slots = c.refine_slots;
+        }
         if (!c.full) {
             static const int rows_per_warp = [] {  // tuning knob (experiments only)
                 const char* e = std::getenv("VSP_FUSED_ROWS_PER_WARP");
@@ -387,7 +437,7 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
         VSP_CUDA(cudaFuncSetAttribute(tridiag_fused_kernel<NQ>, cudaFuncAttributePreferredSharedMemoryCarveout, \
                                       cudaSharedmemCarveoutMaxShared));                                       \
         tridiag_fused_kernel<NQ><<<c.count, 32 * nw, smem, st>>>(p->d_items, c.begin, ws, npad64, rows_smem,  \
-                                                                  debug_timing);                               \
+                                                                  debug_timing, gate);                         \
         break;
                 VSP_FUSED_CASE(1)
                 VSP_FUSED_CASE(2)
@@ -400,16 +450,47 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
         } else {
             const int threads = std::min(1024, c.npad);
             tridiag_global_kernel<<<c.count, threads, tridiag_global_smem_bytes(c.npad), st>>>(p->d_items, c.begin,
-                                                                                              ws, c.npad);
+                                                                                              ws, c.npad, gate);
         }
         g_launches++;
         VSP_CUDA(cudaGetLastError());
         if ((rc = mark()) != VSP_OK) return rc;
+        // The re-solve of the items the tridiagonalisation flagged runs beside the bisection kernel.
+        // Its few fat CTAs (1024 threads, whole SM) must be placed BEFORE the many thin bisection
+        // CTAs flood the SMs, so the re-solve stays on the caller's stream (it starts the moment the
+        // tridiagonalisation drains) and the bisection is the one that forks to the side stream.
+        const bool fork = c.refine_slots > 0;
+        cudaStream_t bst = st;
+        if (fork) {
+            RefinePool pool;
+            pool.base = reinterpret_cast<double*>(refine_base + c.refine_off);
+            pool.slots = c.refine_slots;
+            pool.slot_doubles = c.refine_slot_doubles;
+            const size_t fixed = refine_smem_fixed_bytes(c.npad);
+            const size_t rsm = 227 * 1024;  // everything beyond the fixed scratch holds the trailing block
+            const int xs_doubles = (int)((rsm - fixed) / sizeof(double));
+            VSP_CUDA(cudaEventRecord(p->ev_fork, st));
+            VSP_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+            if (p->dtype == VSP_F32) {
+                VSP_CUDA(cudaFuncSetAttribute(refine_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                refine_kernel<float><<<c.refine_slots, 1024, rsm, st>>>(p->d_items, gate, pool, c.npad, xs_doubles, p->opts, d_sv, d_records);
+            } else {
+                VSP_CUDA(cudaFuncSetAttribute(refine_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                refine_kernel<double><<<c.refine_slots, 1024, rsm, st>>>(p->d_items, gate, pool, c.npad, xs_doubles, p->opts, d_sv, d_records);
+            }
+            g_launches++;
+            VSP_CUDA(cudaGetLastError());
+            bst = p->side;
+        }
         const int bthreads = bisect_threads(c.n);
-        bisect_metrics_kernel<<<c.count, bthreads, bisect_smem_bytes(c.npad), st>>>(p->d_items, c.begin, ws, c.npad,
-                                                                                    p->opts, d_sv, d_records);
+        bisect_metrics_kernel<<<c.count, bthreads, bisect_smem_bytes(c.npad), bst>>>(p->d_items, c.begin, ws, c.npad,
+                                                                                     p->opts, d_sv, d_records);
         g_launches++;
         VSP_CUDA(cudaGetLastError());
+        if (fork) {  // join
+            VSP_CUDA(cudaEventRecord(p->ev_join, p->side));
+            VSP_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0));
+        }
         if ((rc = mark()) != VSP_OK) return rc;
     }
     return VSP_OK;

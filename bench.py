@@ -265,7 +265,7 @@ def run_b200_arm(args) -> None:
     lay = CheckpointLayout.vit(SCENARIO["embed_dim"], SCENARIO["depth"])
     n_ckpt = args.ckpts
     eng = pkg.SpectraEngine(dev)
-    runner = SweepRunner(eng, lay, ckpts_per_chunk=args.chunk)
+    runner = SweepRunner(eng, lay, ckpts_per_chunk=args.chunk, lanes=args.lanes)
 
     # synthetic random-init weights, generated on the device
     arenas = []
@@ -444,7 +444,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ckpts", type=int, default=SCENARIO["epochs"] * len(SCENARIO["seeds"]), help="checkpoints per GPU per step")
-    ap.add_argument("--chunk", type=int, default=8, help="checkpoints per H2D/compute pipeline chunk (e2e)")
+    ap.add_argument("--chunk", type=int, default=12, help="checkpoints per H2D/compute pipeline chunk (e2e)")
+    ap.add_argument("--lanes", type=int, default=4, help="compute lanes the e2e pipeline rotates chunks over")
     ap.add_argument("--ref-ckpts", type=int, default=4, help="checkpoints per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -157,30 +157,36 @@ class SweepRunner:
 
     run_device : arenas already in HBM -> one batched launch sequence.
     run_host   : arenas in pinned host memory -> chunks are copied on a side stream
-                 into two alternating device buffers while the previous chunk is
-                 being analysed; records and singular values come back per chunk.
+                 into rotating device buffers while earlier chunks are being analysed on
+                 rotating compute lanes; records and singular values come back per chunk.
     """
 
-    def __init__(self, engine: SpectraEngine, layout: CheckpointLayout, ckpts_per_chunk: int = 8):
+    def __init__(self, engine: SpectraEngine, layout: CheckpointLayout, ckpts_per_chunk: int = 12, lanes: int = 4):
         self.engine = engine
         self.layout = layout
         self.chunk = max(1, ckpts_per_chunk)
+        self.nlanes = max(1, lanes)
         self._slots: list[torch.Tensor] | None = None
         self._copy_stream: torch.cuda.Stream | None = None
+        # run_host alternates chunks between two compute lanes (engine + stream + workspace each),
+        # so the long tail of one chunk (the FP64 re-solve of an ill-conditioned matrix keeps one SM
+        # busy for milliseconds) overlaps the next chunk's kernels instead of stalling the stream.
+        self._lanes: list[tuple[SpectraEngine, torch.cuda.Stream]] | None = None
         self._pinned: dict[tuple, torch.Tensor] = {}
         self._tables: dict[tuple, tuple] = {}
         self._slot_off = np.array([4 * s.offset for s in layout.slots], dtype=np.uint64)
         self._rows = np.array([s.rows for s in layout.slots], dtype=np.int32)
         self._cols = np.array([s.cols for s in layout.slots], dtype=np.int32)
 
-    def _table(self, nck: int, want_sv: bool):
+    def _table(self, nck: int, want_sv: bool, engine: SpectraEngine | None = None):
         """rows / cols / ld tables and the cached plan for `nck` checkpoints."""
-        key = (nck, want_sv)
+        engine = engine or self.engine
+        key = (nck, want_sv, id(engine))
         t = self._tables.get(key)
         if t is None:
             rows, cols = np.tile(self._rows, nck), np.tile(self._cols, nck)
             ld = cols.astype(np.int64)
-            plan = self.engine.make_plan(rows, cols, ld, nat.VSP_F32, want_sv=want_sv)
+            plan = engine.make_plan(rows, cols, ld, nat.VSP_F32, want_sv=want_sv)
             t = self._tables[key] = (rows, cols, ld, plan)
         return t
 
@@ -212,36 +218,45 @@ class SweepRunner:
         rec_host = self._pin("rec", nck * mats * 64, torch.uint8)
         sv_host = self._pin("sv", nck * n_sv, torch.float64) if want_sv else None
         if self._slots is None or self._slots[0].numel() < self.chunk * lay.arena_elems:
-            self._slots = [torch.empty(self.chunk * lay.arena_elems, dtype=torch.float32, device=dev) for _ in range(2)]
+            self._slots = [torch.empty(self.chunk * lay.arena_elems, dtype=torch.float32, device=dev) for _ in range(self.nlanes)]
             self._copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream(dev)
         copy = self._copy_stream
+        if self._lanes is None:
+            self._lanes = [(eng if k == 0 else SpectraEngine(dev), torch.cuda.Stream(device=dev)) for k in range(self.nlanes)]
         copy.wait_stream(main)
-        free = [None, None]  # event: slot's previous consumer finished
+        for _, cs in self._lanes:
+            cs.wait_stream(main)
+        L = self.nlanes
+        free = [None] * L  # event: slot's previous consumer finished
         keep = []
         for ci, c0 in enumerate(range(0, nck, self.chunk)):
             chunk = arenas[c0 : c0 + self.chunk]
-            slot = self._slots[ci & 1]
+            slot = self._slots[ci % L]
+            lane_eng, lane_stream = self._lanes[ci % L]
             with torch.cuda.stream(copy):
-                if free[ci & 1] is not None:
-                    copy.wait_event(free[ci & 1])
+                if free[ci % L] is not None:
+                    copy.wait_event(free[ci % L])
                 for j, a in enumerate(chunk):
                     slot[j * lay.arena_elems : (j + 1) * lay.arena_elems].copy_(a.view(-1), non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(copy)
-            main.wait_event(ready)
-            rows, cols, ld, plan = self._table(len(chunk), want_sv)
-            bases = np.uint64(slot.data_ptr()) + np.arange(len(chunk), dtype=np.uint64) * np.uint64(lay.bytes)
-            res = eng.analyze_raw(self._ptrs(bases), rows, cols, ld, nat.VSP_F32, want_sv=want_sv, plan=plan)
-            done = torch.cuda.Event()
-            done.record(main)
-            free[ci & 1] = done
-            r0 = c0 * mats * 64
-            rec_host[r0 : r0 + res.records.numel()].copy_(res.records, non_blocking=True)
-            if want_sv:
-                s0 = c0 * n_sv
-                sv_host[s0 : s0 + res.sv.numel()].copy_(res.sv, non_blocking=True)
+            with torch.cuda.stream(lane_stream):
+                lane_stream.wait_event(ready)
+                rows, cols, ld, plan = self._table(len(chunk), want_sv, lane_eng)
+                bases = np.uint64(slot.data_ptr()) + np.arange(len(chunk), dtype=np.uint64) * np.uint64(lay.bytes)
+                res = lane_eng.analyze_raw(self._ptrs(bases), rows, cols, ld, nat.VSP_F32, want_sv=want_sv, plan=plan)
+                done = torch.cuda.Event()
+                done.record(lane_stream)
+                free[ci % L] = done
+                r0 = c0 * mats * 64
+                rec_host[r0 : r0 + res.records.numel()].copy_(res.records, non_blocking=True)
+                if want_sv:
+                    s0 = c0 * n_sv
+                    sv_host[s0 : s0 + res.sv.numel()].copy_(res.sv, non_blocking=True)
             keep.append(res)
+        for _, cs in self._lanes:
+            main.wait_stream(cs)
         main.synchronize()
         rec = rec_host.numpy().view(nat.RECORD_DTYPE).copy()
         for ci, c0 in enumerate(range(0, nck, self.chunk)):  # records carry chunk-local item ids

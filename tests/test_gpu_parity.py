@@ -263,3 +263,20 @@ def test_c_abi_host_entry_and_errors():
     assert lib.vsp_workspace_bytes(count, nat.p32(huge), nat.p32(huge)) == -2  # VSP_E_UNSUPPORTED
     handle = ctypes.c_void_p()
     assert lib.vsp_plan_create(count, nat.p32(rows), nat.p32(cols), None, 7, None, ctypes.byref(handle)) == -2
+
+
+def test_checkpoint_feeder_matches_live_model(engine, tmp_path):
+    """analyze_checkpoint(saved state dict) == extract_and_analyze_weights(live model): same keys,
+    same numbers (bitwise: both reach the kernels as the same fp32 device matrices)."""
+    from vision_spectra_b200.checkpoint import analyze_checkpoint
+    from vision_spectra_b200.experiments.run_spectral_analysis import extract_and_analyze_weights
+
+    model = WrappedViT(embed_dim=96, depth=2, seed=11).cuda()
+    path = tmp_path / "epoch_0003.pt"
+    torch.save({"epoch": 3, "model_state_dict": model.state_dict()}, path)
+    live = extract_and_analyze_weights(model, torch.device("cuda", 0))
+    saved = analyze_checkpoint(path, torch.device("cuda", 0))
+    assert list(saved["per_layer_metrics"]) == list(live["per_layer_metrics"])
+    assert saved["per_layer_metrics"] == live["per_layer_metrics"]
+    assert saved["aggregated_metrics"] == live["aggregated_metrics"]
+    assert saved["singular_values"] == live["singular_values"]

@@ -180,3 +180,29 @@ def test_partition_lpt_and_round_robin():
                 assert all(i in s for i in members) or not any(i in s for i in members)
     assert shard_checkpoints(10, 4, 1) == [1, 5, 9]
     assert sorted(sum((shard_checkpoints(93, 8, r) for r in range(8)), [])) == list(range(93))
+
+
+@pytest.mark.parametrize("make", [
+    lambda: StubViT(embed_dim=32, depth=2, seed=1),
+    lambda: WrappedViT(embed_dim=32, depth=2, seed=2),
+    lambda: StubViT(embed_dim=32, depth=1, seed=3, separate_qkv=True),
+])
+def test_state_dict_selection_matches_module_extraction(make, tmp_path):
+    """checkpoint.select_matrices on a saved state dict == the reference's extraction rules on
+    the live model (names, order, types, layer indices, values), incl. the trainer's union."""
+    from vision_spectra_b200.checkpoint import load_checkpoint, select_matrices
+
+    model = make()
+    path = tmp_path / "ckpt.pt"
+    torch.save({"epoch": 3, "model_state_dict": model.state_dict(), "best_val_metric": 0.5}, path)  # base.py:576-594
+    sd = load_checkpoint(path)
+    ours = select_matrices(sd)
+    ref = orc.extract_qkv_weights(model) + orc.extract_attention_weights(model) + orc.extract_mlp_weights(model)
+    assert [(w.name, w.layer_idx, w.matrix_type, tuple(w.shape)) for w in ours] == [
+        (w.name, w.layer_idx, w.matrix_type, tuple(w.shape)) for w in ref
+    ]
+    for a, b in zip(ours, ref):
+        np.testing.assert_array_equal(a.numpy(), b.weight)
+    ours2 = select_matrices(sd, layer_patterns=["blocks.0"], include_mlp=False, include_patch_embed=True)
+    ref2 = orc.extract_all_weights(model, ["blocks.0"], True, True, False, True)
+    assert [(w.name, w.matrix_type, tuple(w.shape)) for w in ours2] == [(w.name, w.matrix_type, tuple(w.shape)) for w in ref2]

@@ -19,6 +19,7 @@
 #include "eig_kernels.cuh"
 #include "gram_f64.cuh"
 #include "gram_i8.cuh"
+#include "sbr_band.cuh"
 
 using namespace vsp;
 
@@ -418,7 +419,43 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
             gate.slot_items = reinterpret_cast<int*>(refine_base + c.refine_items_off);
             gate.slots = c.refine_slots;
         }
-        if (!c.full) {
+        static const bool use_unblocked = [] {  // experiments: VSP_EIG=fused selects the unblocked reduction
+            const char* e = std::getenv("VSP_EIG");
+            return e && std::string(e) == "fused";
+        }();
+        if (!c.full && !use_unblocked) {
+            // two-stage reduction: blocked Householder to bandwidth 4 (sbr_band.cuh), bulge chasing (band_tridiag.cuh)
+            const int nw = sbr_warps(c.n);
+            const int stv = 32 * nw;  // stride of the [4][stv] operand arrays
+            size_t budget = 0;
+            switch ((nw + 1) / 2) {
+#define VSP_SBR_CASE(HALF, NQ, MINB)                                                                              \
+    case HALF: {                                                                                                  \
+        budget = std::min<size_t>(kSbrSmemBudget, (227 * 1024) / MINB - 1024);                                    \
+        const int rows_smem = sbr_rows_in_smem(c.n, stv, nw, budget);                                              \
+        const size_t smem = sbr_smem_bytes(rows_smem, stv, nw);                                                    \
+        VSP_CUDA(cudaFuncSetAttribute(sbr_band_kernel<NQ, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                      (int)std::max<size_t>(smem, 48 * 1024)));                                   \
+        VSP_CUDA(cudaFuncSetAttribute(sbr_band_kernel<NQ, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,  \
+                                      cudaSharedmemCarveoutMaxShared));                                           \
+        sbr_band_kernel<NQ, MINB><<<c.count, 32 * nw, smem, st>>>(p->d_items, c.begin, ws, stv, rows_smem);        \
+    } break;
+                VSP_SBR_CASE(1, 2, 6)
+                VSP_SBR_CASE(2, 4, 3)
+                VSP_SBR_CASE(3, 6, 2)
+                VSP_SBR_CASE(4, 8, 1)
+#undef VSP_SBR_CASE
+                default:
+                    return VSP_E_UNSUPPORTED;
+            }
+            g_launches++;
+            VSP_CUDA(cudaGetLastError());
+            const size_t csm = band_tridiag_smem_bytes(c.n);
+            VSP_CUDA(cudaFuncSetAttribute(band_tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)std::max<size_t>(csm, 48 * 1024)));
+            band_tridiag_kernel<<<(c.count + kChaseWarps - 1) / kChaseWarps, 32 * kChaseWarps, csm, st>>>(
+                p->d_items, c.begin, c.count, ws, gate);
+        } else if (!c.full) {
             static const int rows_per_warp = [] {  // tuning knob (experiments only)
                 const char* e = std::getenv("VSP_FUSED_ROWS_PER_WARP");
                 const int v = e ? std::atoi(e) : 0;

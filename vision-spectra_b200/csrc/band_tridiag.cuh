@@ -29,9 +29,9 @@
 namespace vsp {
 
 constexpr int kSbrB = 4;        // bandwidth after stage 2a-1
-constexpr int kChaseW = 8;      // stored sub-diagonals + 1 (2b)
+constexpr int kChaseW = 9;      // row stride: 2b stored diagonals + 1 pad (odd stride spreads the rows over the banks)
 constexpr int kChasePadRows = 3 * kSbrB;
-constexpr int kChaseWarps = 4;  // matrices per CTA
+constexpr int kChaseWarps = 3;  // matrices per CTA
 
 __host__ __device__ inline size_t band_tridiag_smem_bytes(int n) {
     return sizeof(double) * (size_t)kChaseWarps * ((size_t)(n + kChasePadRows) * kChaseW + 32);
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(32 * kChaseWarps)
     if (out[2 * n + MISC_FLAGS] != 0.0) return;  // non-finite / all-zero: stage 2a-1 wrote d = e = 0
 
     for (int i = lane; i < rows * kChaseW; i += 32) {
-        const int r = i >> 3, jj = i & 7;
+        const int r = i / kChaseW, jj = i - r * kChaseW;
         double val = 0.0;
         if (r < n && jj <= kSbrB && r - jj >= 0) val = G[band_poff(r) + r - jj];
         L[i] = val;

@@ -41,8 +41,8 @@ __host__ __device__ inline int sbr_warps(int n) {
     int nw = (n + 31) / 32;
     return nw < 1 ? 1 : nw;
 }
-// fixed scratch (doubles): V W U Yown Yoth(=P) [4][st] | T 16 | tau 4 | Zpart [nw][16] | pad 12
-__host__ __device__ inline size_t sbr_fixed_doubles(int st, int nw) { return (size_t)20 * st + 32 + (size_t)16 * nw; }
+// fixed scratch (doubles): V W U Y(=P) [4][st] | T 16 | tau 4 | Zpart [nw][16] | pad 12
+__host__ __device__ inline size_t sbr_fixed_doubles(int st, int nw) { return (size_t)16 * st + 32 + (size_t)16 * nw; }
 constexpr int kSbrPad = 64;  // doubles after the last shared-memory row (masked lanes never read, but keep 16-byte slack)
 __host__ __device__ inline size_t sbr_smem_bytes(int rows_smem, int st, int nw) {
     return sizeof(double) * (sbr_fixed_doubles(st, nw) + (size_t)poff(rows_smem) + kSbrPad);
@@ -58,196 +58,298 @@ __host__ __device__ inline int sbr_rows_in_smem(int n, int st, int nw, size_t bu
 
 #if defined(__CUDACC__)
 
-// 16 values spread over the 8 lanes that differ in lane bits 0..2 -> lane lc keeps the sums 2lc, 2lc+1
-__device__ __forceinline__ void fold16_lc(const double (&a)[16], int lane, double& o0, double& o1) {
-    double b[8], c[4];
-    const bool b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const double send = b2 ? a[j] : a[j + 8], keep = b2 ? a[j + 8] : a[j];
-        b[j] = keep + shfl_xor_d(send, 4);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const double send = b1 ? b[j] : b[j + 4], keep = b1 ? b[j + 4] : b[j];
-        c[j] = keep + shfl_xor_d(send, 2);
-    }
-    {
-        const double send = b0 ? c[0] : c[2], keep = b0 ? c[2] : c[0];
-        o0 = keep + shfl_xor_d(send, 1);
-    }
-    {
-        const double send = b0 ? c[1] : c[3], keep = b0 ? c[3] : c[1];
-        o1 = keep + shfl_xor_d(send, 1);
-    }
-}
-// 16 values spread over the 4 lanes that differ in lane bits 3..4 -> lane lr keeps the sums 4lr..4lr+3
-__device__ __forceinline__ void fold16_lr(const double (&a)[16], int lane, double (&o)[4]) {
-    double b[8];
-    const bool b4 = lane & 16, b3 = lane & 8;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const double send = b4 ? a[j] : a[j + 8], keep = b4 ? a[j + 8] : a[j];
-        b[j] = keep + shfl_xor_d(send, 16);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const double send = b3 ? b[j] : b[j + 4], keep = b3 ? b[j + 4] : b[j];
-        o[j] = keep + shfl_xor_d(send, 8);
-    }
+// FP64 tensor-core MMA (SASS: DMMA.8x8x4), D[8x8] += A[8x4] B[4x8].  Lane (g = lane>>2, t = lane&3) holds
+//   a = A[g][t],  b = B[t][g],  d0 = D[g][2t], d1 = D[g][2t+1].
+// Measured on B200 (scripts/micro/dmma_bench.cu): 37.1 TFLOP/s with one warp per SM sub-partition, the
+// same peak as the DFMA pipe at 1/8 of the instructions, and the k-reduction happens inside the pipe.
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// One 16x32 sub-tile of the fused pass.  Rows R0 + {2lr, 2lr+1, 2lr+8, 2lr+9} (slots 0..3), columns
-// C0 + {2lc, 2lc+1} (half 0) and C0 + 16 + {2lc, 2lc+1} (half 1).  rowacc[slot*4 + k],
-// colacc[(2*half + xy)*4 + k].  Kinds (compile time, so interior tiles carry no masks at all):
-//   kTileFull  off-diagonal, all 16 rows < p0
-//   kTileRows  off-diagonal, last row block: rows >= p0 masked
-//   kTileDiag0 diagonal block, upper sub-tile (R0 == C0): only half 0 exists, triangular mask
-//   kTileDiag1 diagonal block, lower sub-tile (R0 == C0 + 16): half 0 full, half 1 triangular
-// On diagonal tiles elements with column > row do not exist and the diagonal enters the row sums only.
-enum { kTileFull = 0, kTileRows = 1, kTileDiag0 = 2, kTileDiag1 = 3 };
+// ---- pending rank-8 update  A -= V W^T + W V^T,  in 16 x 32 units (rows R0.., columns C0..) of up to 8 tiles.
+// Per 8x8 tile the stored values are the C fragment (lane: row g, columns 2t, 2t+1 = one 128-bit access), the
+// row operands -V[t][row g], -W[t][row g] are A fragments and W[t][col g], V[t][col g] are B fragments: two
+// DMMAs per tile.  Loads and compute are separate so that the sweep can fetch the next unit (possibly from the
+// global workspace, i.e. L2) while the current one is in the pipe.
+struct SbrUnit {
+    int u;       // row-major unit number: 16-row blocks 2a and 2a+1 have a+1 units each
+    int i16, j;  // 16-row block, 32-column block (j <= i16 >> 1)
+    __device__ __forceinline__ bool valid() const { return u >= 0; }
+    __device__ __forceinline__ static int first_of(int i16) {  // number of the first unit of a 16-row block
+        const int a = i16 >> 1;
+        return (i16 & 1) ? (a + 1) * (a + 1) : a * (a + 1);
+    }
+    __device__ __forceinline__ void locate() {  // (i16, j) of unit u; i16 only ever moves down
+        if (u < 0) return;
+        while (first_of(i16) > u) --i16;
+        j = u - first_of(i16);
+    }
+};
 
-template <int KIND, bool DO_UPD, bool DO_SYM>
-__device__ __forceinline__ void sbr_subtile(double* __restrict__ base, int R0, int C0, int p0,
-                                            const double* __restrict__ Vb, const double* __restrict__ Wb,
-                                            const double* __restrict__ Ub, int st, int lr, int lc,
-                                            double (&rowacc)[16], double (&colacc)[16]) {
-    constexpr int NH = (KIND == kTileDiag0) ? 1 : 2;     // halves that exist
-    constexpr bool ROWMASK = (KIND != kTileFull);        // rows may be >= p0
-    constexpr int TRI = (KIND == kTileDiag0) ? 0 : ((KIND == kTileDiag1) ? 1 : -1);  // half with the triangular mask
-    const int rbase = R0 + 2 * lr, cbase = C0 + 2 * lc;
-    const int rr[4] = {rbase, rbase + 1, rbase + 8, rbase + 9};
-    double2 a[4][NH];
-    bool ok[4][NH];  // the double2 (columns cbase + 16h, +1) of row slot s is stored
-    double* rowp[4];
+__device__ __forceinline__ bool sbr_tile_ok(bool diag, int trr, int tc, int g, int t, bool rv) {
+    return rv && (!(diag && tc == trr) || 2 * t <= g);  // diagonal tile: the pair (2t, 2t+1) starts at or left of the diagonal
+}
+
+__device__ __forceinline__ void sbr_unit_load(const double* __restrict__ base, SbrUnit u, int p0, int g, int t,
+                                              double2 (&c)[8]) {
+    const int R0 = 16 * u.i16, C0 = 32 * u.j;
+    const bool diag = u.j == (u.i16 >> 1);
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        rowp[s] = base + poff(rr[s]) + cbase;
+    for (int tr = 0; tr < 2; ++tr) {
+        const int row = R0 + 8 * tr + g;
+        const bool rv = row < p0;
+        const double* rowp = base + poff(row) + C0 + 2 * t;
+        const int trr = 2 * (u.i16 & 1) + tr;  // 8-row block index inside the 32 x 32 block
 #pragma unroll
-        for (int h = 0; h < NH; ++h) {
-            ok[s][h] = (!ROWMASK || rr[s] < p0) && (h != TRI || cbase + 16 * h <= rr[s]);
-            if (ROWMASK || h == TRI)
-                a[s][h] = ok[s][h] ? *reinterpret_cast<const double2*>(rowp[s] + 16 * h) : make_double2(0.0, 0.0);
-            else
-                a[s][h] = *reinterpret_cast<const double2*>(rowp[s] + 16 * h);
+        for (int tc = 0; tc < 4; ++tc) {
+            const bool ok = sbr_tile_ok(diag, trr, tc, g, t, rv) && !(diag && tc > trr);
+            c[tr * 4 + tc] = ok ? *reinterpret_cast<const double2*>(rowp + 8 * tc) : make_double2(0.0, 0.0);
         }
-    }
-    // ---- pending rank-8 update (V = W = 0 before the first panel)
-    if (DO_UPD) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const double2 vr0 = *reinterpret_cast<const double2*>(Vb + k * st + rbase);
-        const double2 vr1 = *reinterpret_cast<const double2*>(Vb + k * st + rbase + 8);
-        const double2 wr0 = *reinterpret_cast<const double2*>(Wb + k * st + rbase);
-        const double2 wr1 = *reinterpret_cast<const double2*>(Wb + k * st + rbase + 8);
-        const double vr[4] = {vr0.x, vr0.y, vr1.x, vr1.y};
-        const double wr[4] = {wr0.x, wr0.y, wr1.x, wr1.y};
-#pragma unroll
-        for (int h = 0; h < NH; ++h) {
-            const double2 vc = *reinterpret_cast<const double2*>(Vb + k * st + cbase + 16 * h);
-            const double2 wc = *reinterpret_cast<const double2*>(Wb + k * st + cbase + 16 * h);
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                a[s][h].x = fma(-wr[s], vc.x, fma(-vr[s], wc.x, a[s][h].x));
-                a[s][h].y = fma(-wr[s], vc.y, fma(-vr[s], wc.y, a[s][h].y));
-            }
-        }
-    }
-#pragma unroll
-    for (int s = 0; s < 4; ++s)
-#pragma unroll
-        for (int h = 0; h < NH; ++h) {
-            if (ROWMASK || h == TRI) {
-                if (ok[s][h]) *reinterpret_cast<double2*>(rowp[s] + 16 * h) = a[s][h];
-            } else {
-                *reinterpret_cast<double2*>(rowp[s] + 16 * h) = a[s][h];
-            }
-        }
-    }
-    // ---- products with the new reflectors: row sums (columns <= row), column sums (columns < row)
-    if (DO_SYM) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const double2 ur0 = *reinterpret_cast<const double2*>(Ub + k * st + rbase);
-        const double2 ur1 = *reinterpret_cast<const double2*>(Ub + k * st + rbase + 8);
-        const double ur[4] = {ur0.x, ur0.y, ur1.x, ur1.y};
-#pragma unroll
-        for (int h = 0; h < NH; ++h) {
-            const double2 uc = *reinterpret_cast<const double2*>(Ub + k * st + cbase + 16 * h);
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                double2 ar = a[s][h], ac = a[s][h];
-                if (h == TRI) {
-                    const int c = cbase + 16 * h;
-                    ar.x = (ok[s][h] && c <= rr[s]) ? a[s][h].x : 0.0;
-                    ar.y = (ok[s][h] && c + 1 <= rr[s]) ? a[s][h].y : 0.0;
-                    ac.x = (ok[s][h] && c < rr[s]) ? a[s][h].x : 0.0;
-                    ac.y = (ok[s][h] && c + 1 < rr[s]) ? a[s][h].y : 0.0;
-                } else if (ROWMASK) {
-                    ar.x = ac.x = ok[s][h] ? a[s][h].x : 0.0;
-                    ar.y = ac.y = ok[s][h] ? a[s][h].y : 0.0;
-                }
-                rowacc[s * 4 + k] = fma(ar.x, uc.x, fma(ar.y, uc.y, rowacc[s * 4 + k]));
-                colacc[(2 * h) * 4 + k] = fma(ac.x, ur[s], colacc[(2 * h) * 4 + k]);
-                colacc[(2 * h + 1) * 4 + k] = fma(ac.y, ur[s], colacc[(2 * h + 1) * 4 + k]);
-            }
-        }
-    }
     }
 }
 
-// dispatch on the kind of the sub-tile and on its address space (rows < rows_smem: shared, else the
-// global workspace, in place)
-template <bool DO_UPD, bool DO_SYM>
-__device__ __forceinline__ void sbr_subtile_at(double* __restrict__ A, double* __restrict__ G, int rows_smem, bool diag,
-                                               int sub, int R0, int C0, int p0, const double* Vb, const double* Wb,
-                                               const double* Ub, int st, int lr, int lc, double (&rowacc)[16],
-                                               double (&colacc)[16]) {
-#define VSP_TILE_ARGS R0, C0, p0, Vb, Wb, Ub, st, lr, lc, rowacc, colacc
-    if (R0 < rows_smem) {
-        if (diag) {
-            if (sub == 0) sbr_subtile<kTileDiag0, DO_UPD, DO_SYM>(A, VSP_TILE_ARGS);
-            else sbr_subtile<kTileDiag1, DO_UPD, DO_SYM>(A, VSP_TILE_ARGS);
-        } else if (R0 + 16 <= p0) {
-            sbr_subtile<kTileFull, DO_UPD, DO_SYM>(A, VSP_TILE_ARGS);
-        } else {
-            sbr_subtile<kTileRows, DO_UPD, DO_SYM>(A, VSP_TILE_ARGS);
-        }
-    } else {
-        if (diag) {
-            if (sub == 0) sbr_subtile<kTileDiag0, DO_UPD, DO_SYM>(G, VSP_TILE_ARGS);
-            else sbr_subtile<kTileDiag1, DO_UPD, DO_SYM>(G, VSP_TILE_ARGS);
-        } else if (R0 + 16 <= p0) {
-            sbr_subtile<kTileFull, DO_UPD, DO_SYM>(G, VSP_TILE_ARGS);
-        } else {
-            sbr_subtile<kTileRows, DO_UPD, DO_SYM>(G, VSP_TILE_ARGS);
+__device__ __forceinline__ void sbr_unit_update(double* __restrict__ base, SbrUnit u, int p0, const double* __restrict__ Vb,
+                                                const double* __restrict__ Wb, int st, int g, int t, double2 (&c)[8]) {
+    const int R0 = 16 * u.i16, C0 = 32 * u.j;
+    const bool diag = u.j == (u.i16 >> 1);
+    double bw[4], bv[4];
+#pragma unroll
+    for (int tc = 0; tc < 4; ++tc) {
+        bw[tc] = Wb[t * st + C0 + 8 * tc + g];
+        bv[tc] = Vb[t * st + C0 + 8 * tc + g];
+    }
+#pragma unroll
+    for (int tr = 0; tr < 2; ++tr) {
+        const int row = R0 + 8 * tr + g;
+        if (R0 + 8 * tr >= p0) continue;  // warp-uniform
+        const bool rv = row < p0;
+        const double av = -Vb[t * st + row], aw = -Wb[t * st + row];
+        double* rowp = base + poff(row) + C0 + 2 * t;
+        const int trr = 2 * (u.i16 & 1) + tr;
+#pragma unroll
+        for (int tc = 0; tc < 4; ++tc) {
+            if (diag && tc > trr) continue;  // above the diagonal: not stored (warp-uniform)
+            dmma(c[tr * 4 + tc].x, c[tr * 4 + tc].y, av, bw[tc]);
+            dmma(c[tr * 4 + tc].x, c[tr * 4 + tc].y, aw, bv[tc]);
+            if (sbr_tile_ok(diag, trr, tc, g, t, rv)) *reinterpret_cast<double2*>(rowp + 8 * tc) = c[tr * 4 + tc];
         }
     }
-#undef VSP_TILE_ARGS
 }
 
-// update-only sweep over the sub-tiles of the leading p0 x p0 triangle: sub-tile number t (row-major over
-// 16-row blocks) is taken by worker (t mod nworkers)
-__device__ __forceinline__ void sbr_update_sweep(double* __restrict__ A, double* __restrict__ G, int rows_smem, int p0,
+// update-only sweep over the units of the leading p0 x p0 triangle, bottom-up (the rows that live in the
+// global workspace first); worker w takes the units w, w + nworkers, ... counted from the last one
+__device__ __noinline__ void sbr_update_sweep(double* __restrict__ A, double* __restrict__ G, int rows_smem, int p0,
                                                  int worker, int nworkers, const double* Vb, const double* Wb, int st,
-                                                 int lr, int lc) {
-    double dummy_r[16], dummy_c[16];
-    int t = 0;
-    const int nrb = (p0 + 15) >> 4;
-    for (int i16 = 0; i16 < nrb; ++i16) {
-        const int jd = i16 >> 1;  // diagonal column block of this row block
-        for (int j = 0; j <= jd; ++j, ++t) {
-            if (t % nworkers != worker) continue;
-            sbr_subtile_at<true, false>(A, G, rows_smem, j == jd, i16 & 1, 16 * i16, 32 * j, p0, Vb, Wb, Vb, st, lr, lc,
-                                        dummy_r, dummy_c);
+                                                 int g, int t) {
+    SbrUnit cur;
+    cur.i16 = ((p0 + 15) >> 4) - 1;
+    cur.u = SbrUnit::first_of(cur.i16) + (cur.i16 >> 1) - worker;  // last unit, minus this worker's offset
+    cur.locate();
+    double2 c[8], cn[8];
+    if (cur.valid()) sbr_unit_load(16 * cur.i16 < rows_smem ? A : G, cur, p0, g, t, c);
+    while (cur.valid()) {
+        SbrUnit nxt = cur;
+        nxt.u -= nworkers;
+        nxt.locate();
+        if (nxt.valid()) sbr_unit_load(16 * nxt.i16 < rows_smem ? A : G, nxt, p0, g, t, cn);
+        sbr_unit_update(16 * cur.i16 < rows_smem ? A : G, cur, p0, Vb, Wb, st, g, t, c);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c[i] = cn[i];
+        cur = nxt;
+    }
+}
+
+// ---- Y = A U contributions of one 8-row strip (rows R0.., columns CB0..CB0+31) of a stored 32 x 32 block:
+//   Dr    += rows:    D[row g][kk] = sum_cols tile[g][col] U[kk][col]     tile as A fragment (C layout: the two
+//                                                                        registers are the k-slices {2t}, {2t+1})
+//   Dc[tc] += columns: D[col g][kk] = sum_rows tile[row][g] U[kk][row]     tile re-read transposed as A fragment
+// (kk = 0..3: the B fragments carry U in the columns n < 4, zero in the rest).  On diagonal tiles elements with
+// column > row do not exist and the diagonal enters the row sums only.
+struct SbrStrip {
+    double2 c[4];
+    double e0[4], e1[4];
+};
+
+__device__ __forceinline__ void sbr_strip_load(const double* __restrict__ base, bool diag, int tr, int R0, int CB0, int p0,
+                                               int g, int t, SbrStrip& sp) {
+    const int row = R0 + g;
+    const bool rv = row < p0;
+    const int r0t = R0 + t, r1t = R0 + 4 + t;
+    const double* rowp = base + poff(row) + CB0 + 2 * t;
+    const double* t0p = base + poff(r0t) + CB0 + g;
+    const double* t1p = base + poff(r1t) + CB0 + g;
+#pragma unroll
+    for (int tc = 0; tc < 4; ++tc) {
+        const bool dt = diag && tc == tr;
+        const bool have = !(diag && tc > tr);
+        sp.c[tc] = (have && rv && (!dt || 2 * t <= g)) ? *reinterpret_cast<const double2*>(rowp + 8 * tc)
+                                                       : make_double2(0.0, 0.0);
+        if (dt && !(2 * t + 1 <= g)) sp.c[tc].y = 0.0;
+        sp.e0[tc] = (have && r0t < p0 && (!dt || g < t)) ? t0p[8 * tc] : 0.0;
+        sp.e1[tc] = (have && r1t < p0 && (!dt || g < 4 + t)) ? t1p[8 * tc] : 0.0;
+    }
+}
+
+__device__ __forceinline__ void sbr_strip_mma(bool diag, int tr, int R0, const double* __restrict__ Ub, int st, int g, int t,
+                                              const double (&bu0)[4], const double (&bu1)[4], const SbrStrip& sp,
+                                              double (&Dr)[2], double (&Dc)[4][2]) {
+    const double bur0 = (g < 4) ? Ub[g * st + R0 + t] : 0.0, bur1 = (g < 4) ? Ub[g * st + R0 + 4 + t] : 0.0;
+#pragma unroll
+    for (int tc = 0; tc < 4; ++tc) {
+        if (diag && tc > tr) continue;  // warp-uniform
+        dmma(Dr[0], Dr[1], sp.c[tc].x, bu0[tc]);
+        dmma(Dr[0], Dr[1], sp.c[tc].y, bu1[tc]);
+        dmma(Dc[tc][0], Dc[tc][1], sp.e0[tc], bur0);
+        dmma(Dc[tc][0], Dc[tc][1], sp.e1[tc], bur1);
+    }
+}
+
+// ---- LQ of the 4 x p0 panel P by one warp, in place in shared memory: four Householder reflectors, row 3 first
+// (pivot column p0-1), then row 2 (pivot p0-2), ...  Lane l works on the column pairs {2l, 2l+1} + 64q.  One
+// butterfly of four values per reflector: |x|^2, the products of x with the rows still to be reduced, and the
+// products of x with the earlier reflectors (they give U^T U, hence T, without a reduction of their own).  Writes
+// U (zero beyond each pivot), T and the R block of the band.  Nothing but scalars lives in registers.
+template <int NP>
+__device__ __forceinline__ void sbr_panel_lq(double* __restrict__ P, double* __restrict__ Ub, double* __restrict__ Tm,
+                                             double* __restrict__ G, int p0, int st, int lane) {
+    double tk[4] = {0.0, 0.0, 0.0, 0.0};
+    double zz[4][4];  // zz[k][j] = u_j . u_k, j < k
+#ifdef VSP_PHASE_TIMING
+    long long lq_t[20];
+    int lq_n = 0;
+    lq_t[lq_n++] = clock64();
+#define VSP_LQ_MARK() lq_t[lq_n++] = clock64()
+#else
+#define VSP_LQ_MARK() ((void)0)
+#endif
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int t = 3 - k;
+        const int pc = p0 - 4 + t;  // pivot column of row t
+        if (pc >= 0) {              // warp-uniform
+            // v[0] = |x|^2, v[1 + t2] = P[t2] . x (t2 < t), v[1 + t + j] = u_j . x (j < k): always four values
+            double v[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const int c0 = 2 * lane + 64 * q;
+                if (c0 < pc) {  // pairs at or beyond the pivot contribute nothing
+                    double2 xm = *reinterpret_cast<const double2*>(P + t * st + c0);
+                    if (c0 + 1 >= pc) xm.y = 0.0;
+                    v[0] = fma(xm.x, xm.x, fma(xm.y, xm.y, v[0]));
+#pragma unroll
+                    for (int t2 = 0; t2 < 3; ++t2)
+                        if (t2 < t) {
+                            const double2 r2 = *reinterpret_cast<const double2*>(P + t2 * st + c0);
+                            v[1 + t2] = fma(r2.x, xm.x, fma(r2.y, xm.y, v[1 + t2]));
+                        }
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        if (j < k) {
+                            const double2 uj = *reinterpret_cast<const double2*>(Ub + j * st + c0);
+                            v[1 + t + j] = fma(uj.x, xm.x, fma(uj.y, xm.y, v[1 + t + j]));
+                        }
+                }
+            }
+            VSP_LQ_MARK();
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[i] += shfl_xor_d(v[i], o);
+            VSP_LQ_MARK();
+            const double xnorm2 = v[0], alpha = P[t * st + pc];
+            double beta = alpha, tau = 0.0, vscale = 0.0;
+            // |x| <= n after the power-of-four scaling; a row below 1e-140 is dropped (set to zero)
+            if (xnorm2 > 1e-280) {
+                const double s2 = fma(alpha, alpha, xnorm2);
+                const double rs = fast_rsqrt(s2);  // 1/||x||
+                const double nrm = s2 * rs;        // ||x||
+                beta = -copysign(nrm, alpha);
+                tau = fma(fabs(alpha), rs, 1.0);  // (beta - alpha)/beta = 1 + |alpha|/||x||
+                vscale = copysign(fast_rcp(fabs(alpha) + nrm), alpha);  // 1/(alpha - beta)
+            }
+            tk[k] = tau;
+            double coef[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int t2 = 0; t2 < 3; ++t2)
+                if (t2 < t) coef[t2] = tau * fma(vscale, v[1 + t2], P[t2 * st + pc]);
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                if (j < k) zz[k][j] = (tau != 0.0) ? fma(vscale, v[1 + t + j], Ub[j * st + pc]) : 0.0;
+            VSP_LQ_MARK();
+            __syncwarp();  // the pivot column has been read by everybody
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const int c0 = 2 * lane + 64 * q;
+                if (c0 < st) {
+                    double2 u = make_double2(0.0, 0.0);
+                    if (c0 <= pc) {
+                        double2 x = *reinterpret_cast<const double2*>(P + t * st + c0);
+                        if (tau != 0.0) {
+                            u.x = (c0 < pc) ? x.x * vscale : 1.0;
+                            u.y = (c0 + 1 < pc) ? x.y * vscale : ((c0 + 1 == pc) ? 1.0 : 0.0);
+                        }
+#pragma unroll
+                        for (int t2 = 0; t2 < 3; ++t2)
+                            if (t2 < t) {
+                                double2 r2 = *reinterpret_cast<const double2*>(P + t2 * st + c0);
+                                r2.x = fma(-coef[t2], u.x, r2.x);
+                                r2.y = fma(-coef[t2], u.y, r2.y);
+                                *reinterpret_cast<double2*>(P + t2 * st + c0) = r2;
+                            }
+                        x.x = (c0 < pc) ? 0.0 : beta;
+                        x.y = (c0 + 1 < pc) ? 0.0 : ((c0 + 1 == pc) ? beta : x.y);
+                        *reinterpret_cast<double2*>(P + t * st + c0) = x;
+                    }
+                    *reinterpret_cast<double2*>(Ub + k * st + c0) = u;
+                }
+            }
+            __syncwarp();
+            VSP_LQ_MARK();
+        } else {
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const int c0 = 2 * lane + 64 * q;
+                if (c0 < st) *reinterpret_cast<double2*>(Ub + k * st + c0) = make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                if (j < k) zz[k][j] = 0.0;
         }
+    }
+#ifdef VSP_PHASE_TIMING
+    if (blockIdx.x == 200 && lane == 0 && (p0 == 92 || p0 == 20)) {
+        printf("[lq p0=%d]", p0);
+        for (int i = 1; i < lq_n; ++i) printf(" %lld", lq_t[i] - lq_t[i - 1]);
+        printf("\n");
+    }
+#endif
+#undef VSP_LQ_MARK
+    // R block -> band output (rows p0+t, columns max(p0-4+t, 0) .. p0-1): 16 entries
+    if (lane < 16) {
+        const int t = lane >> 2, c = p0 - 4 + (lane & 3);
+        if (c >= 0 && c >= p0 - 4 + t) G[poff(p0 + t) + c] = P[t * st + c];
+    }
+    // T from U^T U (forward recurrence in application order)
+    if (lane == 0) {
+        const double t00 = tk[0], t11 = tk[1], t22 = tk[2], t33 = tk[3];
+        const double t01 = -t11 * (t00 * zz[1][0]);
+        const double t02 = -t22 * fma(t01, zz[2][1], t00 * zz[2][0]);
+        const double t12 = -t22 * (t11 * zz[2][1]);
+        const double t03 = -t33 * fma(t02, zz[3][2], fma(t01, zz[3][1], t00 * zz[3][0]));
+        const double t13 = -t33 * fma(t12, zz[3][2], t11 * zz[3][1]);
+        const double t23 = -t33 * (t22 * zz[3][2]);
+        Tm[0] = t00; Tm[1] = t01; Tm[2] = t02; Tm[3] = t03;
+        Tm[4] = 0.0; Tm[5] = t11; Tm[6] = t12; Tm[7] = t13;
+        Tm[8] = 0.0; Tm[9] = 0.0; Tm[10] = t22; Tm[11] = t23;
+        Tm[12] = 0.0; Tm[13] = 0.0; Tm[14] = 0.0; Tm[15] = t33;
     }
 }
 
 // NQ = 32-column chunks a lane of the LQ warp holds (= max warps); MINB = CTAs per SM
 template <int NQ, int MINB>
 __global__ void __launch_bounds__(32 * NQ, MINB)
-    sbr_band_kernel(const ItemDesc* __restrict__ items, int item_base, double* __restrict__ ws, int st, int rows_smem) {
+    sbr_band_kernel(const ItemDesc* __restrict__ items, int item_base, double* __restrict__ ws, int st, int rows_smem,
+                    int m_start, int m_stop) {
     extern __shared__ __align__(16) double smem[];
     const ItemDesc it = items[item_base + blockIdx.x];
     const int n = it.n;
@@ -255,69 +357,79 @@ __global__ void __launch_bounds__(32 * NQ, MINB)
     // warp index broadcast from lane 0: the compiler then knows it is warp-uniform, so the `warp == 0` /
     // `warp < nb` regions are uniform branches and the shuffles inside them are plain SHFLs
     const int lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), NW = nthreads >> 5;
-    const int lr = lane >> 3, lc = lane & 7;
+    const int g = lane >> 2, t = lane & 3;  // DMMA fragment coordinates
 
     double* Vb = smem;            // [4][st] previous reflectors (pending update)
     double* Wb = Vb + 4 * st;     // [4][st] previous W
     double* Ub = Wb + 4 * st;     // [4][st] current reflectors
-    double* Yown = Ub + 4 * st;   // [4][st] sums kept by the owner of an index block
-    double* Yoth = Yown + 4 * st; // [4][st] sums added by the partner warps; doubles as the panel buffer P
+    double* Yoth = Ub + 4 * st;   // [4][st] Y = A U: partner sums during the pass, own sums added at its end; also the panel buffer P
     double* Tm = Yoth + 4 * st;   // [16] T, row-major, upper triangular
     double* tauv = Tm + 16;       // [4] (+12 pad)
     double* Zpart = tauv + 16;    // [NW][16]
     double* A = Zpart + 16 * NW;  // rows < rows_smem (+ kSbrPad)
 
-    // ---- load + condition the Gram matrix (same rules as tridiag_fused_kernel)
+    // The reduction of one matrix may be split over several launches (m_start > 0: resume with the leading
+    // m_start x m_start block, already scaled and up to date in the workspace; m_stop > 0: hand over as soon as the
+    // active order is <= m_stop): the small trailing steps are latency-bound, and a smaller footprint lets more
+    // matrices share an SM.
     double* __restrict__ G = ws + it.gram_off;
-    double md = 0.0;
-    int bad = 0;
-    for (int c = lane; c < n; c += 32) {
-        const double g = G[poff(c) + c];
-        if (!isfinite(g)) bad = 1;
-        md = fmax(md, g);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        md = fmax(md, shfl_xor_d(md, o));
-        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
-    }
     double* out = ws + it.de_off;
-    int flags = 0;
-    double scale = 1.0;
-    if (bad) {
-        flags = VSP_ST_NONFINITE;
-    } else if (!(md > 0.0)) {
-        flags = VSP_ST_ZERO;
+    const int n0 = m_start > 0 ? m_start : n;  // order this launch starts from
+    const int rs_eff = rows_smem < n0 ? rows_smem : n0;
+    const int total = poff(n0), in_smem = poff(rs_eff);
+    if (m_start > 0) {
+        if (out[2 * n + MISC_FLAGS] != 0.0) return;  // non-finite / all-zero: flagged by the first launch
+        for (int i = tid; i < in_smem; i += nthreads) A[i] = G[i];
     } else {
-        int ex;
-        (void)frexp(md, &ex);
-        if (ex & 1) ex += 1;
-        scale = ldexp(1.0, -ex);
-    }
-    if (flags) {  // uniform over the CTA
-        for (int i = tid; i < 2 * n; i += nthreads) out[i] = 0.0;
+        // ---- load + condition the Gram matrix (same rules as tridiag_fused_kernel)
+        double md = 0.0;
+        int bad = 0;
+        for (int c = lane; c < n; c += 32) {
+            const double gd = G[poff(c) + c];
+            if (!isfinite(gd)) bad = 1;
+            md = fmax(md, gd);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            md = fmax(md, shfl_xor_d(md, o));
+            bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+        }
+        int flags = 0;
+        double scale = 1.0;
+        if (bad) {
+            flags = VSP_ST_NONFINITE;
+        } else if (!(md > 0.0)) {
+            flags = VSP_ST_ZERO;
+        } else {
+            int ex;
+            (void)frexp(md, &ex);
+            if (ex & 1) ex += 1;
+            scale = ldexp(1.0, -ex);
+        }
+        if (flags) {  // uniform over the CTA
+            for (int i = tid; i < 2 * n; i += nthreads) out[i] = 0.0;
+            if (tid == 0) {
+                out[2 * n + MISC_SCALE] = 1.0;
+                out[2 * n + MISC_FLAGS] = (double)flags;
+                out[2 * n + MISC_SLOT] = -1.0;
+            }
+            return;
+        }
         if (tid == 0) {
-            out[2 * n + MISC_SCALE] = 1.0;
-            out[2 * n + MISC_FLAGS] = (double)flags;
+            out[2 * n + MISC_SCALE] = scale;
+            out[2 * n + MISC_FLAGS] = 0.0;
             out[2 * n + MISC_SLOT] = -1.0;
         }
-        return;
+        for (int i = tid; i < in_smem; i += nthreads) A[i] = G[i] * scale;
+        for (int i = in_smem + tid; i < total; i += nthreads) G[i] *= scale;  // rows >= rows_smem: in place
     }
-    if (tid == 0) {
-        out[2 * n + MISC_SCALE] = scale;
-        out[2 * n + MISC_FLAGS] = 0.0;
-        out[2 * n + MISC_SLOT] = -1.0;
-    }
-    const int rs_eff = rows_smem < n ? rows_smem : n;
-    const int total = poff(n), in_smem = poff(rs_eff);
-    for (int i = tid; i < in_smem; i += nthreads) A[i] = G[i] * scale;
-    for (int i = in_smem + tid; i < total; i += nthreads) G[i] *= scale;  // rows >= rows_smem: in place
     for (int i = tid; i < kSbrPad; i += nthreads) A[in_smem + i] = 0.0;
-    for (int i = tid; i < 20 * st; i += nthreads) Vb[i] = 0.0;
+    for (int i = tid; i < 16 * st; i += nthreads) Vb[i] = 0.0;
     __syncthreads();
 
 #ifdef VSP_PHASE_TIMING  // per-phase cycle counters of this warp (development builds only)
     long long t_phase[6] = {0, 0, 0, 0, 0, 0};  // mini | LQ (+wait) | pass compute | pass barriers | W-phase | panels
+    long long t_prev[5] = {0, 0, 0, 0, 0};
     long long t_mark = clock64();
 #define VSP_LAP(k)                        \
     do {                                  \
@@ -329,8 +441,8 @@ __global__ void __launch_bounds__(32 * NQ, MINB)
 #define VSP_LAP(k) ((void)0)
 #endif
     bool pending = false;
-    int m = n;
-    while (m >= kSbrB + 2) {
+    int m = n0;
+    while (m >= kSbrB + 2 && m > m_stop) {
         const int p0 = m - kSbrB;
         // ---- (1) mini-pass: panel rows p0..m-1, one column per thread
         double* P = Yoth;
@@ -357,134 +469,20 @@ __global__ void __launch_bounds__(32 * NQ, MINB)
         // ---- (2) LQ of the panel by warp 0, while the other warps apply the pending update to the
         //      leading p0 x p0 triangle (the update does not depend on the new reflectors)
         if (warp != 0) {
-            if (pending) sbr_update_sweep(A, G, rs_eff, p0, warp - 1, NW - 1, Vb, Wb, st, lr, lc);
+            if (pending) sbr_update_sweep(A, G, rs_eff, p0, warp - 1, NW - 1, Vb, Wb, st, g, t);
         } else {
-            double Pr[4][NQ], Uk[4][NQ];
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) {
-                    Pr[t][q] = (32 * q < st) ? P[t * st + lane + 32 * q] : 0.0;
-                    Uk[t][q] = 0.0;
-                }
-            double tk[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int t = 3 - k;
-                const int pc = p0 - 4 + t;  // pivot column of row t
-                if (pc >= 0) {              // warp-uniform
-                    // partial sums over columns < pc: |x|^2 and the products with the rows above
-                    double red[4] = {0.0, 0.0, 0.0, 0.0};  // [0..t-1]: rows t2 < t, [3]: |x|^2   (t <= 3)
-                    double piv[4] = {0.0, 0.0, 0.0, 0.0};  // P[t2][pc], t2 <= t, picked from the owner lane
-#pragma unroll
-                    for (int q = 0; q < NQ; ++q) {
-                        const int c = lane + 32 * q;
-                        const double x = (c < pc) ? Pr[t][q] : 0.0;
-                        red[3] = fma(x, x, red[3]);
-#pragma unroll
-                        for (int t2 = 0; t2 < 3; ++t2)
-                            if (t2 < t) red[t2] = fma(Pr[t2][q], x, red[t2]);
-                        if (c == pc) {
-#pragma unroll
-                            for (int t2 = 0; t2 < 4; ++t2)
-                                if (t2 <= t) piv[t2] = Pr[t2][q];
-                        }
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            red[i] += shfl_xor_d(red[i], o);
-                            piv[i] += shfl_xor_d(piv[i], o);  // one non-zero contribution: a broadcast
-                        }
-                    }
-                    const double xnorm2 = red[3], alpha = piv[t];
-                    double beta = alpha, tau = 0.0, vscale = 0.0;
-                    if (xnorm2 > 0.0) {
-                        const double s2 = fma(alpha, alpha, xnorm2);
-                        if (s2 > 1e-280) {
-                            const double rs = fast_rsqrt(s2);
-                            const double nrm = s2 * rs;
-                            beta = -copysign(nrm, alpha);
-                            tau = fma(fabs(alpha), rs, 1.0);
-                            vscale = copysign(fast_rcp(fabs(alpha) + nrm), alpha);
-                        } else {
-                            beta = -copysign(sqrt(s2), alpha);
-                            tau = (beta - alpha) / beta;
-                            vscale = 1.0 / (alpha - beta);
-                        }
-                    }
-                    tk[k] = tau;
-                    double coef[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-                    for (int t2 = 0; t2 < 3; ++t2)
-                        if (t2 < t) coef[t2] = tau * fma(vscale, red[t2], piv[t2]);
-#pragma unroll
-                    for (int q = 0; q < NQ; ++q) {
-                        const int c = lane + 32 * q;
-                        double u = 0.0;
-                        if (tau != 0.0) u = (c < pc) ? Pr[t][q] * vscale : ((c == pc) ? 1.0 : 0.0);
-                        Uk[k][q] = u;
-#pragma unroll
-                        for (int t2 = 0; t2 < 3; ++t2)
-                            if (t2 < t) Pr[t2][q] = fma(-coef[t2], u, Pr[t2][q]);
-                        if (c < pc) Pr[t][q] = 0.0;
-                        if (c == pc) Pr[t][q] = beta;
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < NQ; ++q)
-                    if (32 * q < st) Ub[k * st + lane + 32 * q] = Uk[k][q];
-            }
-            // R block -> band output (rows p0+t, columns max(p0-4+t, 0) .. p0-1)
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) {
-                    const int c = lane + 32 * q;
-                    if (c < p0 && c >= p0 - 4 + t) G[poff(p0 + t) + c] = Pr[t][q];
-                }
-            // T from U^T U (forward recurrence in application order)
-            double z[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // (0,1) (0,2) (1,2) (0,3) (1,3) (2,3)
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                z[0] = fma(Uk[0][q], Uk[1][q], z[0]);
-                z[1] = fma(Uk[0][q], Uk[2][q], z[1]);
-                z[2] = fma(Uk[1][q], Uk[2][q], z[2]);
-                z[3] = fma(Uk[0][q], Uk[3][q], z[3]);
-                z[4] = fma(Uk[1][q], Uk[3][q], z[4]);
-                z[5] = fma(Uk[2][q], Uk[3][q], z[5]);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                for (int i = 0; i < 6; ++i) z[i] += shfl_xor_d(z[i], o);
-            if (lane == 0) {
-                const double t00 = tk[0], t11 = tk[1], t22 = tk[2], t33 = tk[3];
-                const double t01 = -t11 * (t00 * z[0]);
-                const double t02 = -t22 * fma(t01, z[2], t00 * z[1]);
-                const double t12 = -t22 * (t11 * z[2]);
-                const double t03 = -t33 * fma(t02, z[5], fma(t01, z[4], t00 * z[3]));
-                const double t13 = -t33 * fma(t12, z[5], t11 * z[4]);
-                const double t23 = -t33 * (t22 * z[5]);
-                Tm[0] = t00; Tm[1] = t01; Tm[2] = t02; Tm[3] = t03;
-                Tm[4] = 0.0; Tm[5] = t11; Tm[6] = t12; Tm[7] = t13;
-                Tm[8] = 0.0; Tm[9] = 0.0; Tm[10] = t22; Tm[11] = t23;
-                Tm[12] = 0.0; Tm[13] = 0.0; Tm[14] = 0.0; Tm[15] = t33;
-            }
-            if (NW == 1 && pending) sbr_update_sweep(A, G, rs_eff, p0, 0, 1, Vb, Wb, st, lr, lc);
+            sbr_panel_lq<(NQ + 1) / 2>(P, Ub, Tm, G, p0, st, lane);
+            if (NW == 1 && pending) sbr_update_sweep(A, G, rs_eff, p0, 0, 1, Vb, Wb, st, g, t);
         }
         __syncthreads();
         VSP_LAP(1);
 
-        // ---- (3) fused pass over the leading p0 x p0 triangle
+        // ---- (3) symmetric products Y = A U over the leading p0 x p0 triangle (cyclic block schedule)
         const int nb = (p0 + 31) >> 5;
         {
-            double colacc[16];
-            double ownR0 = 0.0, ownR1 = 0.0, ownR2 = 0.0, ownR3 = 0.0;  // folded row sums of the own block
-            bool flushed = false;
+            double own[4][2];  // sums of the own index block, as D fragments: [8-row/col group][kk = 2t, 2t+1]
 #pragma unroll
-            for (int i = 0; i < 16; ++i) colacc[i] = 0.0;
+            for (int i = 0; i < 4; ++i) own[i][0] = own[i][1] = 0.0;
             const int nsteps = (nb >> 1) + 1;
             for (int s = 0; s < nsteps; ++s) {
                 if (warp < nb) {
@@ -493,56 +491,50 @@ __global__ void __launch_bounds__(32 * NQ, MINB)
                     const bool half = (2 * s == nb);   // the pair {w, w + nb/2} is met from both sides
                     const bool own_cols = (s == 0) || (o > warp);
                     const int rb = own_cols ? o : warp, cb = own_cols ? warp : o;  // stored tile (rb, cb)
-                    if (!own_cols && !flushed) {
-                        // the own block's column sums are complete: fold and publish them
-                        double f[4];
-                        fold16_lr(colacc, lane, f);
-                        const int c = 32 * warp + 2 * lc + (lr & 1) + 16 * (lr >> 1);
+                    const int tr0 = (half && !own_cols) ? 2 : 0, tr1 = (half && own_cols) ? 2 : 4;
+                    const int RB0 = 32 * rb, CB0 = 32 * cb;
+                    // the sums of the own index block accumulate in `own` across the steps, those of the partner
+                    // block in `oth` (added to the shared vector below): own = columns <=> own_cols
+                    double oth[4][2], bu0[4], bu1[4];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) Yown[k * st + c] = f[k];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) colacc[i] = 0.0;
-                        flushed = true;
+                    for (int i = 0; i < 4; ++i) {
+                        oth[i][0] = oth[i][1] = 0.0;
+                        const double2 uu = (g < 4) ? *reinterpret_cast<const double2*>(Ub + g * st + CB0 + 8 * i + 2 * t)
+                                                   : make_double2(0.0, 0.0);
+                        bu0[i] = uu.x;
+                        bu1[i] = uu.y;
                     }
-                    if (!(s > 0 && o == warp)) {  // nb == 1 and s > 0 cannot happen (nsteps == 1), guard anyway
-#pragma unroll 1
-                        for (int sub = 0; sub < 2; ++sub) {
-                            if (half && sub != (own_cols ? 0 : 1)) continue;
-                            const int R0 = 32 * rb + 16 * sub, C0 = 32 * cb;
-                            if (R0 >= p0) continue;
-                            double rowacc[16];
+                    {
+                        int tre = tr1;  // strips [tr0, tre) exist
+                        while (tre > tr0 && RB0 + 8 * (tre - 1) >= p0) --tre;
+                        SbrStrip sp, spn;
+                        if (tr0 < tre)
+                            sbr_strip_load(RB0 + 8 * tr0 < rs_eff ? A : G, s == 0, tr0, RB0 + 8 * tr0, CB0, p0, g, t, sp);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) rowacc[i] = 0.0;
-                            sbr_subtile_at<false, true>(A, G, rs_eff, s == 0, sub, R0, C0, p0, Vb, Wb, Ub, st, lr, lc, rowacc, colacc);
-                            double f0, f1;
-                            fold16_lc(rowacc, lane, f0, f1);  // row slot lc>>1, k = 2(lc&1), 2(lc&1)+1
-                            if (own_cols) {
-                                const int slot = lc >> 1;
-                                const int r = R0 + 2 * lr + (slot & 1) + 8 * (slot >> 1);
-                                const int k0 = 2 * (lc & 1);
-                                if (s == 0) {  // first touch of this block's partner sums: plain store
-                                    Yoth[k0 * st + r] = f0;
-                                    Yoth[(k0 + 1) * st + r] = f1;
-                                } else {
-                                    Yoth[k0 * st + r] += f0;
-                                    Yoth[(k0 + 1) * st + r] += f1;
-                                }
-                            } else if (sub == 0) {
-                                ownR0 += f0;
-                                ownR1 += f1;
-                            } else {
-                                ownR2 += f0;
-                                ownR3 += f1;
-                            }
+                        for (int tr = 0; tr < 4; ++tr) {
+                            if (tr < tr0 || tr >= tre) continue;  // warp-uniform
+                            if (tr + 1 < tre)
+                                sbr_strip_load(RB0 + 8 * (tr + 1) < rs_eff ? A : G, s == 0, tr + 1, RB0 + 8 * (tr + 1), CB0,
+                                               p0, g, t, spn);
+                            if (own_cols)
+                                sbr_strip_mma(s == 0, tr, RB0 + 8 * tr, Ub, st, g, t, bu0, bu1, sp, oth[tr], own);
+                            else
+                                sbr_strip_mma(s == 0, tr, RB0 + 8 * tr, Ub, st, g, t, bu0, bu1, sp, own[tr], oth);
+                            sp = spn;
                         }
-                        if (!own_cols) {  // column sums of the partner block
-                            double f[4];
-                            fold16_lr(colacc, lane, f);
-                            const int c = 32 * cb + 2 * lc + (lr & 1) + 16 * (lr >> 1);
+                    }
+                    // partner block: add to the shared vector (exclusive during this step)
+                    if (t < 2) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) Yoth[k * st + c] += f[k];
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) colacc[i] = 0.0;
+                        for (int i = 0; i < 4; ++i) {
+                            double* y0 = Yoth + (2 * t) * st + 32 * o + 8 * i + g;
+                            if (s == 0) {  // first touch of this block's sums: plain store
+                                y0[0] = oth[i][0];
+                                y0[st] = oth[i][1];
+                            } else {
+                                y0[0] += oth[i][0];
+                                y0[st] += oth[i][1];
+                            }
                         }
                     }
                 }
@@ -550,21 +542,13 @@ __global__ void __launch_bounds__(32 * NQ, MINB)
                 __syncthreads();
                 VSP_LAP(3);
             }
-            if (warp < nb) {
-                if (!flushed) {
-                    double f[4];
-                    fold16_lr(colacc, lane, f);
-                    const int c = 32 * warp + 2 * lc + (lr & 1) + 16 * (lr >> 1);
+            if (warp < nb && t < 2) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) Yown[k * st + c] = f[k];
+                for (int i = 0; i < 4; ++i) {
+                    double* y0 = Yoth + (2 * t) * st + 32 * warp + 8 * i + g;  // all steps are done: exclusive again
+                    y0[0] += own[i][0];
+                    y0[st] += own[i][1];
                 }
-                __syncwarp();
-                const int slot = lc >> 1, k0 = 2 * (lc & 1);
-                const int r = 32 * warp + 2 * lr + (slot & 1) + 8 * (slot >> 1);
-                Yown[k0 * st + r] += ownR0;
-                Yown[(k0 + 1) * st + r] += ownR1;
-                Yown[k0 * st + r + 16] += ownR2;
-                Yown[(k0 + 1) * st + r + 16] += ownR3;
             }
         }
         __syncthreads();
@@ -580,7 +564,7 @@ __global__ void __launch_bounds__(32 * NQ, MINB)
                 double y[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    y[k] = Yown[k * st + r] + Yoth[k * st + r];
+                    y[k] = Yoth[k * st + r];
                     u[k] = Ub[k * st + r];
                 }
 #pragma unroll
@@ -657,6 +641,10 @@ __global__ void __launch_bounds__(32 * NQ, MINB)
         __syncthreads();
         VSP_LAP(4);
 #ifdef VSP_PHASE_TIMING
+        if (blockIdx.x == 200 && tid == 0)
+            printf("[sbr panel] m=%d  cycles: mini %lld LQ %lld pass %lld passbar %lld W %lld\n", m + 4, t_phase[0] - t_prev[0],
+                   t_phase[1] - t_prev[1], t_phase[2] - t_prev[2], t_phase[3] - t_prev[3], t_phase[4] - t_prev[4]);
+        for (int q_ = 0; q_ < 5; ++q_) t_prev[q_] = t_phase[q_];
         t_phase[5] += 1;
 #endif
     }
@@ -666,6 +654,14 @@ __global__ void __launch_bounds__(32 * NQ, MINB)
                t_phase[0], t_phase[1], t_phase[2], t_phase[3], t_phase[4], t_phase[5]);
 #endif
 #undef VSP_LAP
+    if (m >= kSbrB + 2) {
+        // ---- hand-over: bring the leading m x m block up to date and return it to the workspace
+        if (pending) sbr_update_sweep(A, G, rs_eff, m, warp, NW, Vb, Wb, st, g, t);
+        __syncthreads();
+        const int back = poff(rs_eff < m ? rs_eff : m);
+        for (int i = tid; i < back; i += nthreads) G[i] = A[i];
+        return;
+    }
     // ---- remaining rows (m <= 5): inside the band; bring them up to date and publish
     for (int i = tid; i < m * 8; i += nthreads) {
         const int r = i >> 3, c = i & 7;

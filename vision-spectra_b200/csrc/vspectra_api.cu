@@ -424,32 +424,44 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
             return e && std::string(e) == "fused";
         }();
         if (!c.full && !use_unblocked) {
-            // two-stage reduction: blocked Householder to bandwidth 4 (sbr_band.cuh), bulge chasing (band_tridiag.cuh)
-            const int nw = sbr_warps(c.n);
-            const int stv = 32 * nw;  // stride of the [4][stv] operand arrays
-            size_t budget = 0;
-            switch ((nw + 1) / 2) {
+            // two-stage reduction: blocked Householder to bandwidth 4 (sbr_band.cuh), bulge chasing (band_tridiag.cuh).
+            // The blocked stage is launched per order range (n -> 96 -> 48 -> end): a smaller active block means a
+            // smaller CTA, so more matrices share an SM while the steps are latency-bound.
+            static const bool one_launch = std::getenv("VSP_SBR_ONE_LAUNCH") != nullptr;  // experiments
+            int m_start = 0;  // 0: fresh start from n
+            const int stops[3] = {96, 48, 0};
+            for (int si = 0; si < 3; ++si) {
+                const int order = m_start > 0 ? m_start : c.n;
+                int m_stop = one_launch ? 0 : stops[si];
+                if (m_stop > 0 && order < m_stop + 32) continue;  // not worth a launch of its own
+                const int nw = sbr_warps(order);
+                const int stv = 32 * nw;  // stride of the [4][stv] operand arrays
+                switch ((nw + 1) / 2) {
 #define VSP_SBR_CASE(HALF, NQ, MINB)                                                                              \
     case HALF: {                                                                                                  \
-        budget = std::min<size_t>(kSbrSmemBudget, (227 * 1024) / MINB - 1024);                                    \
-        const int rows_smem = sbr_rows_in_smem(c.n, stv, nw, budget);                                              \
-        const size_t smem = sbr_smem_bytes(rows_smem, stv, nw);                                                    \
+        const size_t budget = std::min<size_t>(kSbrSmemBudget, (227 * 1024) / MINB - 1024);                       \
+        const int rows_smem = sbr_rows_in_smem(order, stv, nw, budget);                                           \
+        const size_t smem = sbr_smem_bytes(std::min(rows_smem, order), stv, nw);                                  \
         VSP_CUDA(cudaFuncSetAttribute(sbr_band_kernel<NQ, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                      (int)std::max<size_t>(smem, 48 * 1024)));                                   \
+                                      (int)std::min<size_t>(227 * 1024, std::max<size_t>(budget, 48 * 1024))));   \
         VSP_CUDA(cudaFuncSetAttribute(sbr_band_kernel<NQ, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,  \
                                       cudaSharedmemCarveoutMaxShared));                                           \
-        sbr_band_kernel<NQ, MINB><<<c.count, 32 * nw, smem, st>>>(p->d_items, c.begin, ws, stv, rows_smem);        \
+        sbr_band_kernel<NQ, MINB><<<c.count, 32 * nw, smem, st>>>(p->d_items, c.begin, ws, stv, rows_smem,        \
+                                                                   m_start, m_stop);                              \
     } break;
-                VSP_SBR_CASE(1, 2, 6)
-                VSP_SBR_CASE(2, 4, 3)
-                VSP_SBR_CASE(3, 6, 2)
-                VSP_SBR_CASE(4, 8, 1)
+                    VSP_SBR_CASE(1, 2, 6)
+                    VSP_SBR_CASE(2, 4, 3)
+                    VSP_SBR_CASE(3, 6, 2)
+                    VSP_SBR_CASE(4, 8, 1)
 #undef VSP_SBR_CASE
-                default:
-                    return VSP_E_UNSUPPORTED;
+                    default:
+                        return VSP_E_UNSUPPORTED;
+                }
+                g_launches++;
+                VSP_CUDA(cudaGetLastError());
+                if (m_stop == 0) break;
+                m_start = order - 4 * ((order - m_stop + 3) / 4);  // the order the launch stopped at
             }
-            g_launches++;
-            VSP_CUDA(cudaGetLastError());
             const size_t csm = band_tridiag_smem_bytes(c.n);
             VSP_CUDA(cudaFuncSetAttribute(band_tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)std::max<size_t>(csm, 48 * 1024)));

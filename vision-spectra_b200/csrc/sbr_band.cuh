@@ -159,48 +159,70 @@ __device__ __noinline__ void sbr_update_sweep(double* __restrict__ A, double* __
     }
 }
 
-// ---- Y = A U contributions of one 8-row strip (rows R0.., columns CB0..CB0+31) of a stored 32 x 32 block:
-//   Dr    += rows:    D[row g][kk] = sum_cols tile[g][col] U[kk][col]     tile as A fragment (C layout: the two
-//                                                                        registers are the k-slices {2t}, {2t+1})
-//   Dc[tc] += columns: D[col g][kk] = sum_rows tile[row][g] U[kk][row]     tile re-read transposed as A fragment
+// ---- Y = A U contributions of one stored 32 x 32 block (rows RB0.., columns CB0..), 8-row strips [tr0, tre).
+// All tiles are fetched first (one 128-bit access per tile and lane, C-fragment layout), so a block that lives in
+// the global workspace pays the L2 latency once.  Per tile:
+//   rows:    D[row g][kk] += sum_cols tile[g][col] U[kk][col]   tile as A fragment: its two registers are the
+//                                                              k-slices {2t} and {2t+1}
+//   columns: D[col g][kk] += sum_rows tile[row][g] U[kk][row]   the transposed tile as A fragment, built with four
+//                                                              shuffles per k-slice (rows 0-3 and 4-7)
 // (kk = 0..3: the B fragments carry U in the columns n < 4, zero in the rest).  On diagonal tiles elements with
 // column > row do not exist and the diagonal enters the row sums only.
-struct SbrStrip {
-    double2 c[4];
-    double e0[4], e1[4];
-};
-
-__device__ __forceinline__ void sbr_strip_load(const double* __restrict__ base, bool diag, int tr, int R0, int CB0, int p0,
-                                               int g, int t, SbrStrip& sp) {
-    const int row = R0 + g;
-    const bool rv = row < p0;
-    const int r0t = R0 + t, r1t = R0 + 4 + t;
-    const double* rowp = base + poff(row) + CB0 + 2 * t;
-    const double* t0p = base + poff(r0t) + CB0 + g;
-    const double* t1p = base + poff(r1t) + CB0 + g;
+__device__ __forceinline__ void sbr_symm_block(const double* __restrict__ base, bool diag, int RB0, int CB0, int tr0,
+                                               int tre, int p0, const double* __restrict__ Ub, int st, int lane, int g,
+                                               int t, double (&rowsum)[4][2], double (&colsum)[4][2]) {
+    double2 c[4][4];
 #pragma unroll
-    for (int tc = 0; tc < 4; ++tc) {
-        const bool dt = diag && tc == tr;
-        const bool have = !(diag && tc > tr);
-        sp.c[tc] = (have && rv && (!dt || 2 * t <= g)) ? *reinterpret_cast<const double2*>(rowp + 8 * tc)
-                                                       : make_double2(0.0, 0.0);
-        if (dt && !(2 * t + 1 <= g)) sp.c[tc].y = 0.0;
-        sp.e0[tc] = (have && r0t < p0 && (!dt || g < t)) ? t0p[8 * tc] : 0.0;
-        sp.e1[tc] = (have && r1t < p0 && (!dt || g < 4 + t)) ? t1p[8 * tc] : 0.0;
+    for (int tr = 0; tr < 4; ++tr) {
+        const int row = RB0 + 8 * tr + g;
+        const bool rv = tr >= tr0 && tr < tre && row < p0;
+        const double* rowp = base + poff(row) + CB0 + 2 * t;
+#pragma unroll
+        for (int tc = 0; tc < 4; ++tc) {
+            const bool dt = diag && tc == tr;
+            const bool ok = rv && !(diag && tc > tr) && (!dt || 2 * t <= g);
+            c[tr][tc] = ok ? *reinterpret_cast<const double2*>(rowp + 8 * tc) : make_double2(0.0, 0.0);
+            if (dt && !(2 * t + 1 <= g)) c[tr][tc].y = 0.0;
+        }
     }
-}
-
-__device__ __forceinline__ void sbr_strip_mma(bool diag, int tr, int R0, const double* __restrict__ Ub, int st, int g, int t,
-                                              const double (&bu0)[4], const double (&bu1)[4], const SbrStrip& sp,
-                                              double (&Dr)[2], double (&Dc)[4][2]) {
-    const double bur0 = (g < 4) ? Ub[g * st + R0 + t] : 0.0, bur1 = (g < 4) ? Ub[g * st + R0 + 4 + t] : 0.0;
+    double bu0[4], bu1[4];
 #pragma unroll
-    for (int tc = 0; tc < 4; ++tc) {
-        if (diag && tc > tr) continue;  // warp-uniform
-        dmma(Dr[0], Dr[1], sp.c[tc].x, bu0[tc]);
-        dmma(Dr[0], Dr[1], sp.c[tc].y, bu1[tc]);
-        dmma(Dc[tc][0], Dc[tc][1], sp.e0[tc], bur0);
-        dmma(Dc[tc][0], Dc[tc][1], sp.e1[tc], bur1);
+    for (int i = 0; i < 4; ++i) {
+        const double2 uu = (g < 4) ? *reinterpret_cast<const double2*>(Ub + g * st + CB0 + 8 * i + 2 * t)
+                                   : make_double2(0.0, 0.0);
+        bu0[i] = uu.x;
+        bu1[i] = uu.y;
+    }
+    const int src0 = 4 * t + (g >> 1), src1 = src0 + 16;  // lanes that hold tile[t][g], tile[4 + t][g]
+    const bool odd = g & 1;
+#pragma unroll
+    for (int tr = 0; tr < 4; ++tr) {
+        if (tr < tr0 || tr >= tre) continue;  // warp-uniform
+        const int R0 = RB0 + 8 * tr;
+        const double bur0 = (g < 4) ? Ub[g * st + R0 + t] : 0.0, bur1 = (g < 4) ? Ub[g * st + R0 + 4 + t] : 0.0;
+        double da0 = 0.0, da1 = 0.0, db0 = 0.0, db1 = 0.0;  // two chains for the row sums
+#pragma unroll
+        for (int tc = 0; tc < 4; ++tc) {
+            if (diag && tc > tr) continue;  // warp-uniform
+            if (tc & 1) {
+                dmma(db0, db1, c[tr][tc].x, bu0[tc]);
+                dmma(db0, db1, c[tr][tc].y, bu1[tc]);
+            } else {
+                dmma(da0, da1, c[tr][tc].x, bu0[tc]);
+                dmma(da0, da1, c[tr][tc].y, bu1[tc]);
+            }
+            const double x0 = __shfl_sync(0xffffffffu, c[tr][tc].x, src0), y0 = __shfl_sync(0xffffffffu, c[tr][tc].y, src0);
+            const double x1 = __shfl_sync(0xffffffffu, c[tr][tc].x, src1), y1 = __shfl_sync(0xffffffffu, c[tr][tc].y, src1);
+            double e0 = odd ? y0 : x0, e1 = odd ? y1 : x1;
+            if (diag && tc == tr) {  // strictly below the diagonal only
+                if (!(g < t)) e0 = 0.0;
+                if (!(g < 4 + t)) e1 = 0.0;
+            }
+            dmma(colsum[tc][0], colsum[tc][1], e0, bur0);
+            dmma(colsum[tc][0], colsum[tc][1], e1, bur1);
+        }
+        rowsum[tr][0] += da0 + db0;
+        rowsum[tr][1] += da1 + db1;
     }
 }
 
@@ -495,32 +517,26 @@ __global__ void __launch_bounds__(32 * NQ, MINB)
                     const int RB0 = 32 * rb, CB0 = 32 * cb;
                     // the sums of the own index block accumulate in `own` across the steps, those of the partner
                     // block in `oth` (added to the shared vector below): own = columns <=> own_cols
-                    double oth[4][2], bu0[4], bu1[4];
+                    double oth[4][2];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        oth[i][0] = oth[i][1] = 0.0;
-                        const double2 uu = (g < 4) ? *reinterpret_cast<const double2*>(Ub + g * st + CB0 + 8 * i + 2 * t)
-                                                   : make_double2(0.0, 0.0);
-                        bu0[i] = uu.x;
-                        bu1[i] = uu.y;
-                    }
+                    for (int i = 0; i < 4; ++i) oth[i][0] = oth[i][1] = 0.0;
                     {
                         int tre = tr1;  // strips [tr0, tre) exist
                         while (tre > tr0 && RB0 + 8 * (tre - 1) >= p0) --tre;
-                        SbrStrip sp, spn;
-                        if (tr0 < tre)
-                            sbr_strip_load(RB0 + 8 * tr0 < rs_eff ? A : G, s == 0, tr0, RB0 + 8 * tr0, CB0, p0, g, t, sp);
-#pragma unroll
-                        for (int tr = 0; tr < 4; ++tr) {
-                            if (tr < tr0 || tr >= tre) continue;  // warp-uniform
-                            if (tr + 1 < tre)
-                                sbr_strip_load(RB0 + 8 * (tr + 1) < rs_eff ? A : G, s == 0, tr + 1, RB0 + 8 * (tr + 1), CB0,
-                                               p0, g, t, spn);
-                            if (own_cols)
-                                sbr_strip_mma(s == 0, tr, RB0 + 8 * tr, Ub, st, g, t, bu0, bu1, sp, oth[tr], own);
-                            else
-                                sbr_strip_mma(s == 0, tr, RB0 + 8 * tr, Ub, st, g, t, bu0, bu1, sp, own[tr], oth);
-                            sp = spn;
+                        const double* blk = (RB0 + 8 * tr0 < rs_eff) ? A : G;  // rs_eff is a multiple of 16 or >= p0:
+                        if (tre - tr0 > 2 && RB0 + 16 >= rs_eff && RB0 < rs_eff) {
+                            // the block straddles the two address spaces: two half blocks
+                            if (own_cols) {
+                                sbr_symm_block(A, s == 0, RB0, CB0, tr0, 2, p0, Ub, st, lane, g, t, oth, own);
+                                sbr_symm_block(G, s == 0, RB0, CB0, 2, tre, p0, Ub, st, lane, g, t, oth, own);
+                            } else {
+                                sbr_symm_block(A, s == 0, RB0, CB0, tr0, 2, p0, Ub, st, lane, g, t, own, oth);
+                                sbr_symm_block(G, s == 0, RB0, CB0, 2, tre, p0, Ub, st, lane, g, t, own, oth);
+                            }
+                        } else if (own_cols) {
+                            sbr_symm_block(blk, s == 0, RB0, CB0, tr0, tre, p0, Ub, st, lane, g, t, oth, own);
+                        } else {
+                            sbr_symm_block(blk, s == 0, RB0, CB0, tr0, tre, p0, Ub, st, lane, g, t, own, oth);
                         }
                     }
                     // partner block: add to the shared vector (exclusive during this step)

@@ -38,6 +38,22 @@ FP64_PEAK_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 148 SM x 64 FP64 FMA/clk x 2
 
 
 # --------------------------------------------------------------------------- utils
+def measure_fp64_peak():
+    """FP64 peak of this GPU, measured live with the DMMA.8x8x4 microbenchmark that `build()` compiles
+    (scripts/micro/dmma_bench.cu; MEASURED_PEAKS.json has no FP64 figure).  Falls back to the derived number."""
+    import subprocess
+
+    exe = ROOT / "vision-spectra_b200" / "lib" / "dmma_bench"
+    try:
+        out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60).stdout
+        vals = [float(ln.split(":")[1].split()[0]) for ln in out.splitlines() if ln.startswith("dmma m8n8k4")]
+        if vals:
+            return max(vals), "measured live: FP64 tensor-core (DMMA.8x8x4) microbenchmark, scripts/micro/dmma_bench.cu"
+    except Exception:
+        pass
+    return FP64_PEAK_TFLOPS, "derived: 148 SM x 64 FP64 FMA/clk x 1.965 GHz (no FP64 figure in MEASURED_PEAKS.json)"
+
+
 def load_peaks() -> dict:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -351,13 +367,14 @@ def run_b200_arm(args) -> None:
     # ---------------- roofline of the dominant kernel
     peaks = load_peaks()
     gram_name = "slice_i8_kernel+gram_i8_mma_kernel"  # stage 1: int8-split Gram on tcgen05 (26 exact int8 MMAs per tile)
-    names = [gram_name, "tridiag_fused_kernel", "bisect_metrics_kernel"]
+    eig_name = "sbr_band_kernel+band_tridiag_kernel"  # stage 2a: blocked Householder on DMMA.8x8x4 + bulge chasing
+    names = [gram_name, eig_name, "bisect_metrics_kernel"]
+    fp64_peak, fp64_src = measure_fp64_peak()
     alg = {
         gram_name: {"bound": "hbm", "work": in_bytes / 1e9, "unit": "GB/s", "peak": peaks["hbm_gbs"],
                     "flops": n_ckpt * lay.flops_gram()},
-        "tridiag_fused_kernel": {"bound": "fp64", "work": n_ckpt * lay.flops_tridiag() / 1e12, "unit": "TFLOP/s",
-                                "peak": FP64_PEAK_TFLOPS},
-        "bisect_metrics_kernel": {"bound": "fp64", "work": None, "unit": "TFLOP/s", "peak": FP64_PEAK_TFLOPS},
+        eig_name: {"bound": "fp64", "work": n_ckpt * lay.flops_tridiag() / 1e12, "unit": "TFLOP/s", "peak": fp64_peak},
+        "bisect_metrics_kernel": {"bound": "fp64", "work": None, "unit": "TFLOP/s", "peak": fp64_peak},
     }
     stages = []
     for nm, t in zip(names, stage_ms):
@@ -379,8 +396,8 @@ def run_b200_arm(args) -> None:
         "unit": dom["unit"],
         "frac": dom["frac"],
         "traffic": None,
-        "peak_source": peaks["source"] if dom["bound"] == "hbm" else "derived: 148 SM x 64 FP64 FMA/clk x 1.965 GHz (no FP64 figure in MEASURED_PEAKS.json)",
-        "algorithmic": "4*rows*cols bytes per matrix (hbm) / (4/3) n^3 flops per matrix (fp64 tridiagonalisation); DESIGN.md",
+        "peak_source": peaks["source"] if dom["bound"] == "hbm" else fp64_src,
+        "algorithmic": "4*rows*cols bytes per matrix (hbm) / (4/3) n^3 flops per matrix (fp64 reduction to tridiagonal form); DESIGN.md",
         "hbm_gbs_whole_step": in_bytes / 1e9 / (ms_total / args.steps / 1e3),
         "hbm_frac_whole_step": in_bytes / 1e9 / (ms_total / args.steps / 1e3) / peaks["hbm_gbs"],
     }

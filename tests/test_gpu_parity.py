@@ -280,3 +280,21 @@ def test_checkpoint_feeder_matches_live_model(engine, tmp_path):
     assert saved["per_layer_metrics"] == live["per_layer_metrics"]
     assert saved["aggregated_metrics"] == live["aggregated_metrics"]
     assert saved["singular_values"] == live["singular_values"]
+
+
+def test_band_reduction_order_ladder(engine):
+    """Stage 2a (sbr_band.cuh + band_tridiag.cuh) at every boundary of its decomposition: orders below one
+    panel (n < 6), around the 32-row index blocks, around the launch hand-overs (48, 96, +32), around the
+    shared-memory/L2 split (rows beyond 144 at n > 144) and the one-CTA-per-SM class (192 < n <= 256), square
+    and rectangular, against the oracle's singular values and metrics."""
+    orders = [1, 2, 3, 5, 6, 7, 9, 31, 32, 33, 47, 48, 49, 63, 64, 65, 79, 80, 81, 95, 96, 97, 111, 112, 113, 127, 128,
+              129, 143, 144, 145, 159, 160, 161, 176, 191, 192, 193, 208, 224, 255, 256]
+    rng = np.random.default_rng(2024)
+    host = []
+    for i, n in enumerate(orders):
+        shape = (n, n) if i % 3 == 0 else ((n, n + 17 + i) if i % 3 == 1 else (2 * n + 5, n))
+        host.append(trunc_normal(rng, shape))
+    metrics, svs, rec = engine.analyze([torch.from_numpy(w).cuda() for w in host])
+    for n, w, m, s, r in zip(orders, host, metrics, svs, rec):
+        _check_record(f"order{n}{w.shape}", w, m, s, r, orc.get_spectral_metrics(w), orc.integer_outputs(w),
+                      orc.singular_values(w))

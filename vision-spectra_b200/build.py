@@ -63,7 +63,20 @@ def build_native(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
+    build_micro()
     return LIB
+
+
+def build_micro() -> Path:
+    """FP64 tensor-core peak microbenchmark (bench.py runs it on the GPU box for the roofline denominator)."""
+    src = PKG.parent / "scripts" / "micro" / "dmma_bench.cu"
+    exe = LIB.parent / "dmma_bench"
+    if src.exists():
+        res = subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-o", str(exe), str(src)],
+                             capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed (dmma_bench):\n" + res.stdout + res.stderr)
+    return exe
 
 
 if __name__ == "__main__":

@@ -39,25 +39,6 @@ __host__ __device__ inline size_t band_tridiag_smem_bytes(int n) {
 
 #if defined(__CUDACC__)
 
-__device__ __forceinline__ double chase_rcp(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    r = fma(fma(-x, r, 1.0), r, r);
-    r = fma(fma(-x, r, 1.0), r, r);
-    return r;
-}
-__device__ __forceinline__ double chase_rsqrt(double x) {
-    double r;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    const double hx = 0.5 * x;
-    r = fma(fma(-hx * r, r, 0.5), r, r);
-    r = fma(fma(-hx * r, r, 0.5), r, r);
-    return r;
-}
-
-// poff() of tridiag_fused.cuh: offset of row r in the padded-even packed lower triangle
-__device__ __forceinline__ int band_poff(int r) { return ((r * (r + 1)) >> 1) + ((r + 1) >> 1); }
-
 __global__ void __launch_bounds__(32 * kChaseWarps)
     band_tridiag_kernel(const ItemDesc* __restrict__ items, int item_base, int count, double* __restrict__ ws,
                         RefineGate gate) {
@@ -78,7 +59,7 @@ __global__ void __launch_bounds__(32 * kChaseWarps)
     for (int i = lane; i < rows * kChaseW; i += 32) {
         const int r = i / kChaseW, jj = i - r * kChaseW;
         double val = 0.0;
-        if (r < n && jj <= kSbrB && r - jj >= 0) val = G[band_poff(r) + r - jj];
+        if (r < n && jj <= kSbrB && r - jj >= 0) val = G[poff(r) + r - jj];
         L[i] = val;
     }
     const int g = lane >> 2, q = lane & 3;
@@ -128,11 +109,11 @@ __global__ void __launch_bounds__(32 * kChaseWarps)
                 double beta, tau, vs;
                 const double s2 = fma(x0, x0, xn2);
                 if (s2 > 1e-280) {
-                    const double rs = chase_rsqrt(s2);
+                    const double rs = fast_rsqrt(s2);
                     const double nrm = s2 * rs;
                     beta = -copysign(nrm, x0);
                     tau = fma(fabs(x0), rs, 1.0);
-                    vs = copysign(chase_rcp(fabs(x0) + nrm), x0);
+                    vs = copysign(fast_rcp(fabs(x0) + nrm), x0);
                 } else {
                     beta = -copysign(sqrt(s2), x0);
                     tau = (beta - x0) / beta;

@@ -42,6 +42,32 @@ struct ItemDesc {
 
 VSP_HD int64_t tri(int64_t i) { return (i * (i + 1)) >> 1; }
 
+// offset of row r in the padded-even packed lower triangle: row r starts at tri(r) + (r+1)/2, i.e. rows are
+// padded to an even length so that every row starts 16-byte aligned (the Gram kernels write this layout)
+VSP_HD int poff(int r) { return ((r * (r + 1)) >> 1) + ((r + 1) >> 1); }
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ double shfl_xor_d(double v, int mask) { return __shfl_xor_sync(0xffffffffu, v, mask); }
+
+// 1/x and 1/sqrt(x) for normal positive doubles: hardware seed + two Newton steps
+// (|rel err| ~ 1e-16; the Householder scalars do not need correctly rounded division).
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double hx = 0.5 * x;
+    r = fma(fma(-hx * r, r, 0.5), r, r);
+    r = fma(fma(-hx * r, r, 0.5), r, r);
+    return r;
+}
+#endif
+
 // misc[] slots written by the tridiagonalisation stage
 enum { MISC_SCALE = 0, MISC_FLAGS = 1, MISC_SLOT = 2, MISC_UNUSED1 = 3, MISC_COUNT = 4 };
 

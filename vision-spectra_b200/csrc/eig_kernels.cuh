@@ -1,7 +1,8 @@
 // eig_kernels.cuh -- CTA wrappers around tridiag.cuh / bisect_metrics.cuh.
 //
-//   tridiag_fused_kernel  n <= kSmemMaxN : (tridiag_fused.cuh) Gram (packed lower) copied
-//                         into shared memory once, reduced there, only d/e go back.
+//   sbr_band_kernel +     n <= kSmemMaxN : (sbr_band.cuh, band_tridiag.cuh) Gram (packed lower) held in shared
+//   band_tridiag_kernel                    memory, blocked Householder reduction to bandwidth 4 on the FP64
+//                                          tensor cores, then pipelined bulge chasing to (d, e).
 //   tridiag_global_kernel larger n       : Gram (full, symmetric) reduced in place in
 //                         global memory / L2 with coalesced column walks.
 //   bisect_metrics_kernel all n          : d/e -> sorted eigenvalues -> singular values,
@@ -11,7 +12,7 @@
 #include "bisect_metrics.cuh"
 #include "refine_bidiag.cuh"
 #include "tridiag.cuh"
-#include "tridiag_fused.cuh"
+#include "sbr_band.cuh"
 
 namespace vsp {
 

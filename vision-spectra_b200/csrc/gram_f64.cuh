@@ -10,7 +10,7 @@
 #pragma once
 
 #include "common.cuh"
-#include "tridiag_fused.cuh"
+#include "common.cuh"  // poff()
 
 namespace vsp {
 
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) gram_f64_kernel(const ItemDesc* __restric
                     G[(int64_t)i * n + j] = acc[r][c];
                     G[(int64_t)j * n + i] = acc[r][c];
                 } else {
-                    G[poff(i) + j] = acc[r][c];  // padded-even packed rows (tridiag_fused.cuh)
+                    G[poff(i) + j] = acc[r][c];  // padded-even packed rows (common.cuh: poff)
                 }
             }
         }

@@ -31,7 +31,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
-#include "tridiag_fused.cuh"  // poff()
+#include "common.cuh"  // poff()
 
 namespace vsp {
 

@@ -1,38 +1,41 @@
-// sbr_band.cuh -- stage 2a-1, n <= kSmemMaxN: blocked Householder reduction of the (scaled)
-// Gram matrix to a symmetric band of bandwidth b = 4, in place.  band_tridiag.cuh finishes the
-// job.  Together they replace the unblocked tridiag_fused.cuh on the product path: the unblocked
-// reduction moves every stored element through shared memory once per *column* (4 DFMA per
-// 16 bytes: shared-memory bound at <= 50 % of the FP64 pipe); here an element moves once per
-// *panel of four columns* and sees 16 DFMA per 16 bytes, so the pass is FP64-bound.
+// sbr_band.cuh -- stage 2a-1, n <= kSmemMaxN: blocked Householder reduction of the (scaled) Gram matrix to a
+// symmetric band of bandwidth b = 4, in place, on the FP64 tensor cores.  band_tridiag.cuh finishes the job.
 //
-// Elimination order is bottom-up (as in tridiag_fused.cuh): the active matrix is the leading
-// m x m block.  One panel step, with p0 = m - 4:
+// Why blocked: an unblocked tridiagonalisation moves every stored element through shared memory once per
+// *column* (4 DFMA per 16 bytes: shared-memory bound at <= 50 % of the FP64 pipe, and one block-wide dependency
+// chain per column).  Here an element moves once per *panel of four columns*, all O(n^3) work is rank-8 updates
+// and 4-column symmetric products, i.e. small GEMMs that run as DMMA.8x8x4 (37.1 TFLOP/s measured on B200 with
+// one warp per SM sub-partition, scripts/micro/dmma_bench.cu), and the serial chain is per panel.
+//
+// Elimination order is bottom-up: the active matrix is the leading m x m block.  One panel step, p0 = m - 4:
 //   (1) mini-pass  (all threads) rows p0..m-1 get the pending rank-8 update  A -= V W^T + W V^T;
-//                  their diagonal block goes to the band output, the b x p0 block left of it to P.
+//                  their diagonal block goes to the band output, the 4 x p0 block left of it to P.
 //   (2) LQ         (warp 0) four Householder reflectors (row p0+3 first, pivot column p0-1, then
 //                  p0+2 / p0-2, ...) reduce P to an upper-triangular 4x4 block R next to the diagonal
-//                  block: Q = H_0 H_1 H_2 H_3 = I - U T U^T (compact WY, T built from U^T U).
-//   (3) pass       (all warps) over the leading p0 x p0 triangle, once:
-//                      A -= V W^T + W V^T   (pending update of the previous panel, 8 DFMA/element)
-//                      Y  = A U             (symmetric, both triangles from one read, 8 DFMA/element)
+//                  block: Q = H_0 H_1 H_2 H_3 = I - U T U^T (compact WY, T from U^T U).
+//       update     (warps 1..) meanwhile the pending update is applied to the leading p0 x p0 triangle: it does not
+//                  need the new reflectors, so the one-warp LQ chain hides behind it.  Two DMMAs per 8x8 tile.
+//   (3) products   (all warps) Y = A U over the leading p0 x p0 triangle, both triangles from one read of the
+//                  stored one: four DMMAs per 8x8 tile (b = 4 fills half of the MMA's n = 8).
 //   (4) W-phase    X = Y T,  S = T^T (U^T X),  W = X - U S / 2;  V <- U.
 //
-// Pass decomposition: index blocks of 32; warp w owns block w.  At step s = 0..nb/2 warp w works
-// on the block pair {w, (w+s) mod nb} (stored tile = rows max, columns min), so in every step all
-// row blocks and all column blocks in flight are distinct: the sums for the *own* block stay in
-// registers for the whole pass, the sums for the *other* block are added to a shared vector that
-// no other warp touches during that step (no atomics, no per-warp scratch).  A 32x32 tile is two
-// 16x32 sub-tiles; a lane holds 4 rows x 4 columns (lr = lane>>3 picks rows {2lr,2lr+1,2lr+8,2lr+9},
-// lc = lane&7 picks columns {2lc,2lc+1,2lc+16,2lc+17}): every operand load is a conflict-free
-// LDS.128 that 4 or 8 lanes share, 112 shared-memory wavefronts per 256 DFMA warp-instructions.
+// Decomposition of (3): index blocks of 32; warp w owns block w.  At step s = 0..nb/2 warp w works on the block
+// pair {w, (w+s) mod nb} (stored tile = rows max, columns min), so in every step all row blocks and all column
+// blocks in flight are distinct: the sums for the *own* block stay in registers for the whole pass, the sums for
+// the *other* block are added to a shared vector that no other warp touches during that step (no atomics, no
+// per-warp scratch).  The stored values of an 8x8 tile are its C fragment (lane (g, t): row g, columns 2t, 2t+1,
+// one 128-bit access); the same two registers are the A fragments of the k-slices {2t} and {2t+1} for the row
+// sums, and four shuffles per slice give the transposed A fragments for the column sums.
 //
-// Rows that do not fit into the CTA's shared memory (two CTAs per SM) stay in the global
-// workspace and are updated in place through L2 -- once per panel instead of once per column.
+// Rows that do not fit into the CTA's shared memory (two CTAs per SM while the active order is large) stay in
+// the global workspace and are updated in place through L2 -- once per panel, with the next unit's tiles
+// fetched while the current one is in the pipe.  The host launches the kernel per order range (n -> 96 -> 48 ->
+// end, vspectra_api.cu): a smaller active block means a smaller CTA and more matrices per SM while the steps
+// are latency-bound.
 #pragma once
 
 #include "band_tridiag.cuh"
 #include "common.cuh"
-#include "tridiag_fused.cuh"  // poff, fast_rcp, fast_rsqrt, shfl_xor_d
 
 namespace vsp {
 
@@ -251,26 +254,28 @@ __device__ __forceinline__ void sbr_panel_lq(double* __restrict__ P, double* __r
         if (pc >= 0) {              // warp-uniform
             // v[0] = |x|^2, v[1 + t2] = P[t2] . x (t2 < t), v[1 + t + j] = u_j . x (j < k): always four values
             double v[4] = {0.0, 0.0, 0.0, 0.0};
+            // branch-free over the column chunks (all loads are issued together); pairs at or beyond the pivot
+            // are masked, chunks beyond the buffer re-read its last pair
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
                 const int c0 = 2 * lane + 64 * q;
-                if (c0 < pc) {  // pairs at or beyond the pivot contribute nothing
-                    double2 xm = *reinterpret_cast<const double2*>(P + t * st + c0);
-                    if (c0 + 1 >= pc) xm.y = 0.0;
-                    v[0] = fma(xm.x, xm.x, fma(xm.y, xm.y, v[0]));
+                const int cl = c0 < st ? c0 : st - 2;
+                double2 xm = *reinterpret_cast<const double2*>(P + t * st + cl);
+                xm.x = (c0 < pc) ? xm.x : 0.0;
+                xm.y = (c0 + 1 < pc) ? xm.y : 0.0;
+                v[0] = fma(xm.x, xm.x, fma(xm.y, xm.y, v[0]));
 #pragma unroll
-                    for (int t2 = 0; t2 < 3; ++t2)
-                        if (t2 < t) {
-                            const double2 r2 = *reinterpret_cast<const double2*>(P + t2 * st + c0);
-                            v[1 + t2] = fma(r2.x, xm.x, fma(r2.y, xm.y, v[1 + t2]));
-                        }
+                for (int t2 = 0; t2 < 3; ++t2)
+                    if (t2 < t) {
+                        const double2 r2 = *reinterpret_cast<const double2*>(P + t2 * st + cl);
+                        v[1 + t2] = fma(r2.x, xm.x, fma(r2.y, xm.y, v[1 + t2]));
+                    }
 #pragma unroll
-                    for (int j = 0; j < 3; ++j)
-                        if (j < k) {
-                            const double2 uj = *reinterpret_cast<const double2*>(Ub + j * st + c0);
-                            v[1 + t + j] = fma(uj.x, xm.x, fma(uj.y, xm.y, v[1 + t + j]));
-                        }
-                }
+                for (int j = 0; j < 3; ++j)
+                    if (j < k) {
+                        const double2 uj = *reinterpret_cast<const double2*>(Ub + j * st + cl);
+                        v[1 + t + j] = fma(uj.x, xm.x, fma(uj.y, xm.y, v[1 + t + j]));
+                    }
             }
             VSP_LQ_MARK();
 #pragma unroll
@@ -302,26 +307,24 @@ __device__ __forceinline__ void sbr_panel_lq(double* __restrict__ P, double* __r
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
                 const int c0 = 2 * lane + 64 * q;
-                if (c0 < st) {
-                    double2 u = make_double2(0.0, 0.0);
-                    if (c0 <= pc) {
-                        double2 x = *reinterpret_cast<const double2*>(P + t * st + c0);
-                        if (tau != 0.0) {
-                            u.x = (c0 < pc) ? x.x * vscale : 1.0;
-                            u.y = (c0 + 1 < pc) ? x.y * vscale : ((c0 + 1 == pc) ? 1.0 : 0.0);
-                        }
+                const int cl = c0 < st ? c0 : st - 2;
+                const bool live = c0 < st;
+                double2 x = *reinterpret_cast<const double2*>(P + t * st + cl);
+                double2 u;
+                u.x = (tau == 0.0 || c0 > pc) ? 0.0 : ((c0 < pc) ? x.x * vscale : 1.0);
+                u.y = (tau == 0.0 || c0 + 1 > pc) ? 0.0 : ((c0 + 1 < pc) ? x.y * vscale : 1.0);
 #pragma unroll
-                        for (int t2 = 0; t2 < 3; ++t2)
-                            if (t2 < t) {
-                                double2 r2 = *reinterpret_cast<const double2*>(P + t2 * st + c0);
-                                r2.x = fma(-coef[t2], u.x, r2.x);
-                                r2.y = fma(-coef[t2], u.y, r2.y);
-                                *reinterpret_cast<double2*>(P + t2 * st + c0) = r2;
-                            }
-                        x.x = (c0 < pc) ? 0.0 : beta;
-                        x.y = (c0 + 1 < pc) ? 0.0 : ((c0 + 1 == pc) ? beta : x.y);
-                        *reinterpret_cast<double2*>(P + t * st + c0) = x;
+                for (int t2 = 0; t2 < 3; ++t2)
+                    if (t2 < t) {
+                        double2 r2 = *reinterpret_cast<const double2*>(P + t2 * st + cl);
+                        r2.x = fma(-coef[t2], u.x, r2.x);
+                        r2.y = fma(-coef[t2], u.y, r2.y);
+                        if (live) *reinterpret_cast<double2*>(P + t2 * st + c0) = r2;
                     }
+                x.x = (c0 < pc) ? 0.0 : ((c0 == pc) ? beta : x.x);
+                x.y = (c0 + 1 < pc) ? 0.0 : ((c0 + 1 == pc) ? beta : x.y);
+                if (live) {
+                    *reinterpret_cast<double2*>(P + t * st + c0) = x;
                     *reinterpret_cast<double2*>(Ub + k * st + c0) = u;
                 }
             }
@@ -403,7 +406,8 @@ __global__ void __launch_bounds__(32 * NQ, MINB)
         if (out[2 * n + MISC_FLAGS] != 0.0) return;  // non-finite / all-zero: flagged by the first launch
         for (int i = tid; i < in_smem; i += nthreads) A[i] = G[i];
     } else {
-        // ---- load + condition the Gram matrix (same rules as tridiag_fused_kernel)
+        // ---- load + condition the Gram matrix (power-of-four scale so that |G_ij| <= 1 and the singular values
+        //      un-scale exactly; NaN/Inf anywhere in W shows on the Gram diagonal)
         double md = 0.0;
         int bad = 0;
         for (int c = lane; c < n; c += 32) {

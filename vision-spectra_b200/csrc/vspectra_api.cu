@@ -19,7 +19,6 @@
 #include "eig_kernels.cuh"
 #include "gram_f64.cuh"
 #include "gram_i8.cuh"
-#include "sbr_band.cuh"
 
 using namespace vsp;
 
@@ -419,11 +418,7 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
             gate.slot_items = reinterpret_cast<int*>(refine_base + c.refine_items_off);
             gate.slots = c.refine_slots;
         }
-        static const bool use_unblocked = [] {  // experiments: VSP_EIG=fused selects the unblocked reduction
-            const char* e = std::getenv("VSP_EIG");
-            return e && std::string(e) == "fused";
-        }();
-        if (!c.full && !use_unblocked) {
+        if (!c.full) {
             // two-stage reduction: blocked Householder to bandwidth 4 (sbr_band.cuh), bulge chasing (band_tridiag.cuh).
             // The blocked stage is launched per order range (n -> 96 -> 48 -> end): a smaller active block means a
             // smaller CTA, so more matrices share an SM while the steps are latency-bound.
@@ -467,35 +462,6 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
                                           (int)std::max<size_t>(csm, 48 * 1024)));
             band_tridiag_kernel<<<(c.count + kChaseWarps - 1) / kChaseWarps, 32 * kChaseWarps, csm, st>>>(
                 p->d_items, c.begin, c.count, ws, gate);
-        } else if (!c.full) {
-            static const int rows_per_warp = [] {  // tuning knob (experiments only)
-                const char* e = std::getenv("VSP_FUSED_ROWS_PER_WARP");
-                const int v = e ? std::atoi(e) : 0;
-                return v > 0 ? v : 24;
-            }();
-            static const int debug_timing = std::getenv("VSP_DEBUG_TIMING") ? 1 : 0;
-            const int nw = fused_warps(c.n, rows_per_warp);
-            const int npad64 = round_up(c.n, 64);  // lanes address column pairs up to 64*NP - 1
-            const int rows_smem = fused_rows_in_smem(c.n, npad64, nw);
-            const size_t smem = tridiag_fused_smem_bytes(rows_smem, npad64, nw);
-            switch ((c.n + 63) / 64) {
-#define VSP_FUSED_CASE(NQ)                                                                                    \
-    case NQ:                                                                                                  \
-        VSP_CUDA(cudaFuncSetAttribute(tridiag_fused_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                      (int)kFusedSmemBudget));                                                \
-        VSP_CUDA(cudaFuncSetAttribute(tridiag_fused_kernel<NQ>, cudaFuncAttributePreferredSharedMemoryCarveout, \
-                                      cudaSharedmemCarveoutMaxShared));                                       \
-        tridiag_fused_kernel<NQ><<<c.count, 32 * nw, smem, st>>>(p->d_items, c.begin, ws, npad64, rows_smem,  \
-                                                                  debug_timing, gate);                         \
-        break;
-                VSP_FUSED_CASE(1)
-                VSP_FUSED_CASE(2)
-                VSP_FUSED_CASE(3)
-                VSP_FUSED_CASE(4)
-#undef VSP_FUSED_CASE
-                default:
-                    return VSP_E_UNSUPPORTED;
-            }
         } else {
             const int threads = std::min(1024, c.npad);
             tridiag_global_kernel<<<c.count, threads, tridiag_global_smem_bytes(c.npad), st>>>(p->d_items, c.begin,

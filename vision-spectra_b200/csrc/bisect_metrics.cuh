@@ -27,11 +27,14 @@ struct TriInfo {
 };
 
 // 2^(1023 - biased_exponent(max(|a|,|b|))): multiplying by it brings the pair back to O(1).
-VSP_DEV double rescale_factor(double a, double b) {
+// `e2` accumulates the binary exponent of the factors, so that the caller can recover the true
+// magnitude of the Sturm terms: p_true = p_scaled * 2^(-e2).
+VSP_DEV double rescale_factor(double a, double b, int& e2) {
 #if defined(__CUDA_ARCH__)
     int ea = (__double2hiint(a) >> 20) & 0x7ff, eb = (__double2hiint(b) >> 20) & 0x7ff;
     int ex = ea > eb ? ea : eb;
     if (ex == 0 || ex == 0x7ff) return 1.0;
+    e2 += 1023 - ex;
     return __hiloint2double((2046 - ex) << 20, 0);
 #else
     int ea, eb;
@@ -39,8 +42,13 @@ VSP_DEV double rescale_factor(double a, double b) {
     (void)frexp(b, &eb);
     if (a == 0.0 && b == 0.0) return 1.0;
     int ex = (a == 0.0) ? eb : (b == 0.0 ? ea : (ea > eb ? ea : eb));
+    e2 += 1 - ex;
     return ldexp(1.0, 1 - ex);
 #endif
+}
+VSP_DEV double rescale_factor(double a, double b) {
+    int unused = 0;
+    return rescale_factor(a, b, unused);
 }
 
 // Sign-change bookkeeping on the integer pipe: the high words of consecutive Sturm terms
@@ -93,17 +101,21 @@ VSP_DEV void sturm_step(const DE r, double xa, double xb, double& a0, double& a1
     b1 = b2;
 }
 
-VSP_DEV void sturm_count2(const DE* de, int n, double xa, double xb, int& na, int& nb) {
+// Also returns the last Sturm term p_n(x) = det(T - x I) of each shift as (mantissa f, exponent e):
+// p_n = f * 2^(-e).  Its sign is (-1)^count; bisect_all interpolates on it once a bracket is isolating.
+VSP_DEV void sturm_count2(const DE* de, int n, double xa, double xb, int& na, int& nb, double& fa, int& ea,
+                          double& fb, int& eb) {
     double a0 = 1.0, a1 = de[0].d - xa;
     double b0 = 1.0, b1 = de[0].d - xb;
     SignCounter ca, cb;
     ca.push(1.0, a1);
     cb.push(1.0, b1);
+    int xa2 = 0, xb2 = 0;
     int i = 1;
     for (int blk = 0; i + 8 <= n; i += 8, ++blk) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) sturm_step(de[i + k], xa, xb, a0, a1, b0, b1, ca, cb);
-        const double sa = rescale_factor(a0, a1), sb = rescale_factor(b0, b1);
+        const double sa = rescale_factor(a0, a1, xa2), sb = rescale_factor(b0, b1, xb2);
         a0 *= sa;
         a1 *= sa;
         b0 *= sb;
@@ -120,6 +132,15 @@ VSP_DEV void sturm_count2(const DE* de, int n, double xa, double xb, int& na, in
     cb.flush();
     na = ca.count;
     nb = cb.count;
+    fa = a1;
+    ea = xa2;
+    fb = b1;
+    eb = xb2;
+}
+VSP_DEV void sturm_count2(const DE* de, int n, double xa, double xb, int& na, int& nb) {
+    double fa, fb;
+    int ea, eb;
+    sturm_count2(de, n, xa, xb, na, nb, fa, ea, fb, eb);
 }
 
 template <class Ctx>
@@ -145,43 +166,124 @@ VSP_DEV TriInfo tri_bounds(Ctx& ctx, const double* d, const double* e, int n) {
     return t;
 }
 
-// lam[k], k = 0..n-1 ascending.  Work item t handles eigenvalues t and t + ceil(n/2).
-// Returns the largest iteration count used by this work item.
-template <class Ctx>
-VSP_DEV int bisect_all(Ctx& ctx, const DE* de, int n, const TriInfo& t, double* lam) {
-    int maxit = 0;
-    const int half = (n + 1) >> 1;
-    for (int k = ctx.tid; k < half; k += ctx.nthreads) {
-        const int kb = k + half;  // may be == n (odd n): then the second slot mirrors the first
-        const bool has_b = kb < n;
-        double lo_a = t.gl, hi_a = t.gu, lo_b = t.gl, hi_b = t.gu;
-        bool done_a = false, done_b = !has_b;
-        int it = 0;
-        for (; it < 128 && !(done_a && done_b); ++it) {
-            const double mid_a = 0.5 * (lo_a + hi_a), mid_b = 0.5 * (lo_b + hi_b);
-            if (!done_a) {
-                const double tol = fmax(t.atol, 4.440892098500626e-16 * fmax(fabs(lo_a), fabs(hi_a)));
-                done_a = (hi_a - lo_a <= tol) || mid_a <= lo_a || mid_a >= hi_a;
-            }
-            if (!done_b) {
-                const double tol = fmax(t.atol, 4.440892098500626e-16 * fmax(fabs(lo_b), fabs(hi_b)));
-                done_b = (hi_b - lo_b <= tol) || mid_b <= lo_b || mid_b >= hi_b;
-            }
-            if (done_a && done_b) break;
-            int na, nb;
-            sturm_count2(de, n, mid_a, mid_b, na, nb);
-            if (!done_a) {
-                if (na >= k + 1) hi_a = mid_a; else lo_a = mid_a;
-            }
-            if (!done_b) {
-                if (nb >= kb + 1) hi_b = mid_b; else lo_b = mid_b;
-            }
-        }
-        lam[k] = 0.5 * (lo_a + hi_a);
-        if (has_b) lam[kb] = 0.5 * (lo_b + hi_b);
-        maxit = it > maxit ? it : maxit;
+// Bracket of one eigenvalue (index k, ascending): count(lo) <= k < count(hi).  Bisection on the counts until
+// the bracket holds exactly one eigenvalue; from then on det(T - x I) changes sign exactly once inside it and
+// the next shift comes from false position with the Illinois weights (superlinear), clamped `tol` away from
+// the ends so that the bracket itself collapses to the tolerance (the stopping rule is the same as for plain
+// bisection), with a bisection step after three interpolated shifts in a row that failed to halve the width.
+// The counts alone decide which end moves: the interpolation only proposes shifts.
+struct Bracket {
+    double lo, hi, flo, fhi;
+    int elo, ehi, clo, chi, side, slow;
+    bool have_lo, have_hi, done, interp;
+
+    VSP_DEV void init(double gl, double gu, int n, bool active) {
+        lo = gl;
+        hi = gu;
+        flo = fhi = 0.0;
+        elo = ehi = 0;
+        clo = 0;
+        chi = n;
+        side = 0;
+        have_lo = have_hi = false;
+        done = !active;
+        slow = 0;
+        interp = false;
     }
-    return maxit;
+    VSP_DEV double tolerance(double atol) const { return fmax(atol, 4.440892098500626e-16 * fmax(fabs(lo), fabs(hi))); }
+    // next shift; sets `done` when the bracket has collapsed
+    VSP_DEV double next(double atol) {
+        const double mid = 0.5 * (lo + hi);
+        interp = false;
+        if (done) return mid;
+        const double tol = tolerance(atol), width = hi - lo;
+        if (width <= tol || mid <= lo || mid >= hi) {
+            done = true;
+            return mid;
+        }
+        // The spectrum of a Gram matrix is non-negative and spans many orders of magnitude.  While the bracket
+        // is wide on the logarithmic scale (hi > 2 lo), search the magnitude geometrically -- 3 bits per step
+        // from above while it still reaches (almost) down to zero, then geometric means -- instead of one bit
+        // per arithmetic halving; det(T - x I) is far from linear across such a bracket, so no interpolation yet.
+        if (hi > 0.0 && !(hi <= 2.0 * lo)) {
+            const double x = (lo > 0.015625 * hi) ? sqrt(lo * hi) : ((lo > 0.0) ? fmax(sqrt(lo * hi), 0.125 * hi) : 0.125 * hi);
+            if (x > lo && x < hi && hi - x > tol && x - lo > tol) return x;
+            return mid;
+        }
+        if (chi - clo != 1 || !have_lo || !have_hi || (flo < 0.0) == (fhi < 0.0) || slow >= 3 || width <= 4.0 * tol) {
+            slow = 0;
+            return mid;
+        }
+        int de = ehi - elo;
+        de = de > 1000 ? 1000 : (de < -1000 ? -1000 : de);
+        const double r = ldexp(flo / fhi, de);  // f(lo) / f(hi) < 0
+        const double tt = r / (r - 1.0);
+        if (!(tt > 0.0 && tt < 1.0)) return mid;
+        double x = fma(tt, width, lo);
+        x = fmax(x, lo + tol);
+        x = fmin(x, hi - tol);
+        if (!(x > lo && x < hi)) return mid;
+        interp = true;
+        return x;
+    }
+    VSP_DEV void update(double x, int cnt, double f, int e, int k) {
+        if (done) return;
+        const double wold = hi - lo;
+        if (cnt >= k + 1) {
+            hi = x;
+            chi = cnt;
+            fhi = f;
+            ehi = e;
+            have_hi = true;
+            if (side > 0) flo *= 0.5;  // the low end survived twice: Illinois
+            side = 1;
+        } else {
+            lo = x;
+            clo = cnt;
+            flo = f;
+            elo = e;
+            have_lo = true;
+            if (side < 0) fhi *= 0.5;
+            side = -1;
+        }
+        // an interpolated shift that failed to halve the bracket counts as slow; three in a row force a bisection
+        slow = (interp && hi - lo > 0.5 * wold) ? slow + 1 : 0;
+    }
+};
+
+// lam[k], k = 0..n-1 ascending.  Every work item runs two brackets at a time (two independent FP64 chains);
+// a bracket that has converged takes the next eigenvalue index from the shared counter `*next_k` (zeroed by the
+// caller before the call), so that lanes whose eigenvalues converge early keep working instead of idling until
+// the slowest lane of their warp is done.  Returns the number of Sturm evaluations of this work item.
+template <class Ctx>
+VSP_DEV int bisect_all(Ctx& ctx, const DE* de, int n, const TriInfo& t, double* lam, int* next_k) {
+    int ka = ctx.fetch_add(next_k), kb = ctx.fetch_add(next_k);
+    Bracket A, B;
+    A.init(t.gl, t.gu, n, ka < n);
+    B.init(t.gl, t.gu, n, kb < n);
+    int it = 0;
+    for (; it < 100000; ++it) {
+        double xa = A.next(t.atol), xb = B.next(t.atol);
+        if (A.done && ka < n) {
+            lam[ka] = xa;  // next() returned the midpoint of the collapsed bracket
+            ka = ctx.fetch_add(next_k);
+            A.init(t.gl, t.gu, n, ka < n);
+            xa = A.next(t.atol);
+        }
+        if (B.done && kb < n) {
+            lam[kb] = xb;
+            kb = ctx.fetch_add(next_k);
+            B.init(t.gl, t.gu, n, kb < n);
+            xb = B.next(t.atol);
+        }
+        if (ka >= n && kb >= n) break;
+        int na, nb, ea, eb;
+        double fa, fb;
+        sturm_count2(de, n, xa, xb, na, nb, fa, ea, fb, eb);
+        A.update(xa, na, fa, ea, ka);
+        B.update(xb, nb, fb, eb, kb);
+    }
+    return it;
 }
 
 // Gram route: lambda_min <= ratio * lambda_max (kappa >~ 3e4) marks the matrix for the re-solve

@@ -103,6 +103,7 @@ struct HostCtx {
     void sum4(double (&v)[4]) { (void)v; }
     int sum_i(int v) { return v; }
     int max_i(int v) { return v; }
+    int fetch_add(int* p) { return (*p)++; }
 };
 #else
 // --------------------------------------------------------------------- device CTA
@@ -190,6 +191,7 @@ struct CtaCtx {
     }
     __device__ __forceinline__ int sum_i(int v) { return (int)(sum((double)v) + 0.5); }
     __device__ __forceinline__ int max_i(int v) { return (int)max((double)v); }
+    __device__ __forceinline__ int fetch_add(int* p) { return atomicAdd(p, 1); }  // p in shared memory
 };
 #endif
 

@@ -22,10 +22,10 @@ __host__ __device__ inline size_t tridiag_global_smem_bytes(int npad) {
     return sizeof(double) * (5 * (size_t)npad + CtaCtx::kScratchDoubles);
 }
 __host__ __device__ inline size_t bisect_smem_bytes(int npad) {
-    return sizeof(double) * (5 * (size_t)npad + CtaCtx::kScratchDoubles);
+    return sizeof(double) * (5 * (size_t)npad + CtaCtx::kScratchDoubles + 2);  // + the eigenvalue work counter
 }
-__host__ __device__ inline int bisect_threads(int n) {  // two eigenvalues per thread
-    int t = (((n + 1) >> 1) + 31) & ~31;
+__host__ __device__ inline int bisect_threads(int n) {  // two brackets per thread, ~1.5 eigenvalues per bracket
+    int t = ((n + 2) / 3 + 31) & ~31;
     return t > 1024 ? 1024 : (t < 32 ? 32 : t);
 }
 
@@ -85,7 +85,10 @@ __global__ void tridiag_global_kernel(const ItemDesc* __restrict__ items, int it
     }
 }
 
-__global__ void bisect_metrics_kernel(const ItemDesc* __restrict__ items, int item_base,
+// MAXT / MINB: launch bounds.  The Sturm recurrences are two dependent FP64 chains per thread, i.e. latency-bound:
+// the small-order instantiation caps the registers so that 8 CTAs (24+ warps) share an SM.
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) bisect_metrics_kernel(const ItemDesc* __restrict__ items, int item_base,
                                       const double* __restrict__ ws, int npad, vsp_opts opts,
                                       double* __restrict__ sv_out, vsp_record* __restrict__ records) {
     extern __shared__ __align__(16) double smem[];
@@ -114,8 +117,10 @@ __global__ void bisect_metrics_kernel(const ItemDesc* __restrict__ items, int it
             de[i].d = d[i];
             de[i].e2 = (i > 0) ? fmax(e[i - 1] * e[i - 1], kE2Floor) : 0.0;
         }
+        int* next_k = reinterpret_cast<int*>(lam + 3 * npad);  // after (d_i, e2_i): the eigenvalue work counter
+        if (ctx.tid == 0) *next_k = 0;
         ctx.sync();
-        iters = bisect_all(ctx, de, n, t, lam);
+        iters = bisect_all(ctx, de, n, t, lam, next_k);
     } else {
         for (int i = ctx.tid; i < n; i += ctx.nthreads) lam[i] = 0.0;
     }

@@ -394,7 +394,8 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
 
     // per-device attribute; cheap enough to set on every call (one process may drive several GPUs)
     VSP_CUDA(cudaFuncSetAttribute(tridiag_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    VSP_CUDA(cudaFuncSetAttribute(bisect_metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VSP_CUDA(cudaFuncSetAttribute(bisect_metrics_kernel<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VSP_CUDA(cudaFuncSetAttribute(bisect_metrics_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 
     auto mark = [&]() -> int {
         if (!evs) return VSP_OK;
@@ -498,8 +499,12 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
             bst = p->side;
         }
         const int bthreads = bisect_threads(c.n);
-        bisect_metrics_kernel<<<c.count, bthreads, bisect_smem_bytes(c.npad), bst>>>(p->d_items, c.begin, ws, c.npad,
-                                                                                     p->opts, d_sv, d_records);
+        if (bthreads <= 128)
+            bisect_metrics_kernel<128, 6><<<c.count, bthreads, bisect_smem_bytes(c.npad), bst>>>(p->d_items, c.begin, ws, c.npad,
+                                                                                                 p->opts, d_sv, d_records);
+        else
+            bisect_metrics_kernel<1024, 1><<<c.count, bthreads, bisect_smem_bytes(c.npad), bst>>>(p->d_items, c.begin, ws, c.npad,
+                                                                                                  p->opts, d_sv, d_records);
         g_launches++;
         VSP_CUDA(cudaGetLastError());
         if (fork) {  // join

@@ -293,7 +293,7 @@ def run_b200_arm(args) -> None:
     in_bytes = n_ckpt * lay.bytes
 
     def step_device():
-        res = runner.run_device(arenas, want_sv=True)
+        res = runner.run_device(arenas, want_sv=True, pipelined=args.pipelined_device)
         out = gather_records(res.records) if world > 1 else res.records
         return res, out
 
@@ -463,6 +463,8 @@ def main():
     ap.add_argument("--ckpts", type=int, default=SCENARIO["epochs"] * len(SCENARIO["seeds"]), help="checkpoints per GPU per step")
     ap.add_argument("--chunk", type=int, default=12, help="checkpoints per H2D/compute pipeline chunk (e2e)")
     ap.add_argument("--lanes", type=int, default=4, help="compute lanes the e2e pipeline rotates chunks over")
+    ap.add_argument("--pipelined-device", action="store_true",
+                    help="device-resident arm: split the batch over the compute lanes too (measured slower than one launch sequence: 228k vs 243k matrices/s)")
     ap.add_argument("--ref-ckpts", type=int, default=4, help="checkpoints per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

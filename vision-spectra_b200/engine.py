@@ -146,6 +146,8 @@ class SpectraEngine:
         want_sv: bool = True,
         plan: int | None = None,
         stage_ms: list | None = None,
+        out_records: torch.Tensor | None = None,
+        out_sv: torch.Tensor | None = None,
     ) -> BatchResult:
         """Table form of analyze_device: `ptrs` is a uint64 array of device addresses,
         rows/cols int32, ld int64 (elements).  The caller keeps the memory alive until
@@ -160,8 +162,11 @@ class SpectraEngine:
         if self._ws is None or self._ws.numel() < ws_bytes:
             self._ws = None
             self._ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=self.device)
-        records = torch.empty(count * nat.RECORD_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
-        sv = torch.empty(int(sv_count), dtype=torch.float64, device=self.device) if want_sv else None
+        # caller-provided output slices (a pipelined sweep writes its chunks into one buffer) or fresh ones
+        records = out_records if out_records is not None else torch.empty(count * nat.RECORD_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
+        sv = (out_sv if out_sv is not None else torch.empty(int(sv_count), dtype=torch.float64, device=self.device)) if want_sv else None
+        if records.numel() != count * nat.RECORD_DTYPE.itemsize or (sv is not None and sv.numel() != int(sv_count)):
+            raise ValueError("analyze_raw: output buffers do not match the batch")
         stream = torch.cuda.current_stream(self.device).cuda_stream
         args = (
             plan,

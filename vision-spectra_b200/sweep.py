@@ -199,15 +199,53 @@ class SweepRunner:
             buf = self._pinned[(tag, dtype)] = torch.empty(numel, dtype=dtype).pin_memory()
         return buf[:numel]
 
-    def run_device(self, arenas: list[torch.Tensor], want_sv: bool = True, stage_ms: list | None = None) -> BatchResult:
-        """All checkpoints in one launch sequence; pointer tables are built with NumPy
-        (one data_ptr() per arena), not per-matrix Python."""
+    def _ensure_lanes(self):
+        dev = self.engine.device
+        if self._lanes is None:
+            self._lanes = [(self.engine if k == 0 else SpectraEngine(dev), torch.cuda.Stream(device=dev)) for k in range(self.nlanes)]
+        return self._lanes
+
+    def run_device(self, arenas: list[torch.Tensor], want_sv: bool = True, stage_ms: list | None = None,
+                   pipelined: bool = False) -> BatchResult:
+        """Arenas already in HBM.  Default: all checkpoints in one launch sequence; pointer tables are built
+        with NumPy (one data_ptr() per arena), not per-matrix Python.  `pipelined=True` splits the batch into
+        `lanes` chunks that run on rotating compute lanes (engine + stream + workspace each), so that the tail
+        of one chunk -- the FP64 re-solve of a few ill-conditioned matrices keeps a handful of SMs busy for
+        milliseconds after everything else has drained -- overlaps the next chunk's (or the next call's)
+        kernels; the chunks write straight into one record / singular-value buffer."""
         for a in arenas:
             if a.dtype != torch.float32 or a.device != self.engine.device or a.numel() < self.layout.arena_elems or not a.is_contiguous():
                 raise ValueError("run_device: arenas must be contiguous float32 tensors of the layout's size on the engine device")
-        rows, cols, ld, plan = self._table(len(arenas), want_sv)
         bases = np.array([a.data_ptr() for a in arenas], dtype=np.uint64)
-        return self.engine.analyze_raw(self._ptrs(bases), rows, cols, ld, nat.VSP_F32, want_sv=want_sv, plan=plan, stage_ms=stage_ms)
+        nck = len(arenas)
+        if not pipelined or stage_ms is not None or self.nlanes < 2 or nck < 2 * self.nlanes:
+            rows, cols, ld, plan = self._table(nck, want_sv)
+            return self.engine.analyze_raw(self._ptrs(bases), rows, cols, ld, nat.VSP_F32, want_sv=want_sv, plan=plan, stage_ms=stage_ms)
+        dev = self.engine.device
+        mats = self.layout.matrices
+        n_sv = sum(min(sl.rows, sl.cols) for sl in self.layout.slots)
+        records = torch.empty(nck * mats * nat.RECORD_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        sv = torch.empty(nck * n_sv, dtype=torch.float64, device=dev) if want_sv else None
+        main = torch.cuda.current_stream(dev)
+        lanes = self._ensure_lanes()
+        per = (nck + self.nlanes - 1) // self.nlanes
+        for li, c0 in enumerate(range(0, nck, per)):
+            lane_eng, lane_stream = lanes[li % self.nlanes]
+            cnt = min(per, nck - c0)
+            lane_stream.wait_stream(main)
+            with torch.cuda.stream(lane_stream):
+                rows, cols, ld, plan = self._table(cnt, want_sv, lane_eng)
+                lane_eng.analyze_raw(self._ptrs(bases[c0 : c0 + cnt]), rows, cols, ld, nat.VSP_F32, want_sv=want_sv, plan=plan,
+                                     out_records=records[c0 * mats * 64 : (c0 + cnt) * mats * 64],
+                                     out_sv=None if sv is None else sv[c0 * n_sv : (c0 + cnt) * n_sv])
+                if c0:  # records carry chunk-local item ids: first int32 of every 64-byte record
+                    records[c0 * mats * 64 : (c0 + cnt) * mats * 64].view(torch.int32).view(-1, 16)[:, 0] += c0 * mats
+        for _, cs in lanes:
+            main.wait_stream(cs)
+        rows_all, cols_all = np.tile(self._rows, nck), np.tile(self._cols, nck)
+        offs = np.zeros(nck * mats + 1, np.int64)
+        np.cumsum(np.minimum(rows_all, cols_all), out=offs[1:])
+        return BatchResult(records, sv, offs, nck * mats)
 
     def run_host(self, arenas: list[torch.Tensor], want_sv: bool = True) -> tuple[np.ndarray, np.ndarray | None]:
         eng, lay = self.engine, self.layout
@@ -222,8 +260,7 @@ class SweepRunner:
             self._copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream(dev)
         copy = self._copy_stream
-        if self._lanes is None:
-            self._lanes = [(eng if k == 0 else SpectraEngine(dev), torch.cuda.Stream(device=dev)) for k in range(self.nlanes)]
+        self._ensure_lanes()
         copy.wait_stream(main)
         for _, cs in self._lanes:
             cs.wait_stream(main)

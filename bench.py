@@ -54,6 +54,15 @@ def measure_fp64_peak():
     return FP64_PEAK_TFLOPS, "derived: 148 SM x 64 FP64 FMA/clk x 1.965 GHz (no FP64 figure in MEASURED_PEAKS.json)"
 
 
+def load_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r01_traffic.json)."""
+    try:
+        t = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
+        return {"bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"], "kernel": t["kernel"], "source": t["source"]}
+    except Exception:
+        return None
+
+
 def load_peaks() -> dict:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -395,7 +404,7 @@ def run_b200_arm(args) -> None:
         "peak": dom["peak"],
         "unit": dom["unit"],
         "frac": dom["frac"],
-        "traffic": None,
+        "traffic": load_traffic(),
         "peak_source": peaks["source"] if dom["bound"] == "hbm" else fp64_src,
         "algorithmic": "4*rows*cols bytes per matrix (hbm) / (4/3) n^3 flops per matrix (fp64 reduction to tridiagonal form); DESIGN.md",
         "hbm_gbs_whole_step": in_bytes / 1e9 / (ms_total / args.steps / 1e3),

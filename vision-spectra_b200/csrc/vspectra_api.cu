@@ -425,8 +425,21 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
             // smaller CTA, so more matrices share an SM while the steps are latency-bound.
             static const bool one_launch = std::getenv("VSP_SBR_ONE_LAUNCH") != nullptr;  // experiments
             int m_start = 0;  // 0: fresh start from n
-            const int stops[3] = {96, 48, 0};
-            for (int si = 0; si < 3; ++si) {
+            static const std::vector<int> stops = [] {  // experiments: VSP_SBR_STOPS="144,96,48"
+                std::vector<int> v;
+                if (const char* e = std::getenv("VSP_SBR_STOPS")) {
+                    for (const char* q = e; *q;) {
+                        v.push_back(std::atoi(q));
+                        while (*q && *q != ',') ++q;
+                        if (*q == ',') ++q;
+                    }
+                } else {
+                    v = {96, 48};
+                }
+                v.push_back(0);
+                return v;
+            }();
+            for (size_t si = 0; si < stops.size(); ++si) {
                 const int order = m_start > 0 ? m_start : c.n;
                 int m_stop = one_launch ? 0 : stops[si];
                 if (m_stop > 0 && order < m_stop + 32) continue;  // not worth a launch of its own

@@ -384,12 +384,16 @@ __global__ void __launch_bounds__(192, 1)
                     __syncwarp();
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(drainbar) : "memory");
                 }
-                if (i < n) {
+                // column exponents of this 16-column group: one load per lane, then shuffles (a per-element global
+                // load here sits on the critical path between two tiles' MMAs)
+                const int jl = nt * kI8TileN + cc * 16 + (lane & 15);
+                const int Ejl = (jl < n) ? E[jl] : 1;
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) {
+                for (int k = 0; k < 16; ++k) {
+                    const int Ej = __shfl_sync(0xffffffffu, Ejl, k);
+                    if (i < n) {
                         const int j = nt * kI8TileN + cc * 16 + k;
                         if (j <= i) {
-                            const int Ej = E[j];
                             double g;
                             if (Ei == 255 || Ej == 255) {
                                 g = __longlong_as_double(0x7ff8000000000000LL);  // NaN/Inf in the input row

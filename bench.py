@@ -351,7 +351,14 @@ def run_b200_arm(args) -> None:
     sync_all()
 
     # ---------------- end to end from pinned host memory ("e2e")
-    host_arenas = [a.cpu().pin_memory() for a in arenas]
+    # one pinned host block; the sweep API takes per-checkpoint arenas (views of it)
+    host_block = torch.empty(n_ckpt * lay.arena_elems, dtype=torch.float32).pin_memory()
+    host_arenas = []
+    for c, a in enumerate(arenas):
+        v = host_block[c * lay.arena_elems : (c + 1) * lay.arena_elems]
+        v.copy_(a[: lay.arena_elems])
+        host_arenas.append(v)
+    torch.cuda.synchronize(dev)
     for _ in range(max(1, args.warmup // 2)):
         runner.run_host(host_arenas, want_sv=True)
     sync_all()
@@ -470,8 +477,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ckpts", type=int, default=SCENARIO["epochs"] * len(SCENARIO["seeds"]), help="checkpoints per GPU per step")
-    ap.add_argument("--chunk", type=int, default=12, help="checkpoints per H2D/compute pipeline chunk (e2e)")
-    ap.add_argument("--lanes", type=int, default=4, help="compute lanes the e2e pipeline rotates chunks over")
+    ap.add_argument("--chunk", type=int, default=8, help="checkpoints per H2D/compute pipeline chunk (e2e)")
+    ap.add_argument("--lanes", type=int, default=6, help="compute lanes the e2e pipeline rotates chunks over")
     ap.add_argument("--pipelined-device", action="store_true",
                     help="device-resident arm: split the batch over the compute lanes too (measured slower than one launch sequence: 228k vs 243k matrices/s)")
     ap.add_argument("--ref-ckpts", type=int, default=4, help="checkpoints per step of the reference arm")

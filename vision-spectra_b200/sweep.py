@@ -161,7 +161,7 @@ class SweepRunner:
                  rotating compute lanes; records and singular values come back per chunk.
     """
 
-    def __init__(self, engine: SpectraEngine, layout: CheckpointLayout, ckpts_per_chunk: int = 12, lanes: int = 4):
+    def __init__(self, engine: SpectraEngine, layout: CheckpointLayout, ckpts_per_chunk: int = 8, lanes: int = 6):
         self.engine = engine
         self.layout = layout
         self.chunk = max(1, ckpts_per_chunk)
@@ -274,8 +274,24 @@ class SweepRunner:
             with torch.cuda.stream(copy):
                 if free[ci % L] is not None:
                     copy.wait_event(free[ci % L])
-                for j, a in enumerate(chunk):
-                    slot[j * lay.arena_elems : (j + 1) * lay.arena_elems].copy_(a.view(-1), non_blocking=True)
+                # consecutive views of one pinned host block go over the bus as ONE copy (55 GB/s measured for
+                # large copies vs 48 GB/s for 10.6 MB ones); separate tensors as one copy each
+                j = 0
+                while j < len(chunk):
+                    a = chunk[j]
+                    k = 1
+                    base = a._base
+                    if base is not None and base.dim() == 1 and a.is_contiguous():
+                        while (j + k < len(chunk) and chunk[j + k]._base is base and chunk[j + k].is_contiguous()
+                               and chunk[j + k].storage_offset() == a.storage_offset() + k * lay.arena_elems
+                               and a.numel() == lay.arena_elems):
+                            k += 1
+                    if k > 1:
+                        o = a.storage_offset() - base.storage_offset()
+                        slot[j * lay.arena_elems : (j + k) * lay.arena_elems].copy_(base[o : o + k * lay.arena_elems], non_blocking=True)
+                    else:
+                        slot[j * lay.arena_elems : (j + 1) * lay.arena_elems].copy_(a.view(-1), non_blocking=True)
+                    j += k
                 ready = torch.cuda.Event()
                 ready.record(copy)
             with torch.cuda.stream(lane_stream):

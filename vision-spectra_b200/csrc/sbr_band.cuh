@@ -510,7 +510,13 @@ __global__ void __launch_bounds__(32 * NQ, MINB)
 #pragma unroll
             for (int i = 0; i < 4; ++i) own[i][0] = own[i][1] = 0.0;
             const int nsteps = (nb >> 1) + 1;
+            // The partner sums of step s go to buffer s mod 3: besides Y itself, the buffers of the previous V and W
+            // are free from here to the W-phase (the update sweep and the mini-pass were their last readers).  Every
+            // step touches every block of its buffer exactly once, so steps 0..2 store, need no barrier between them
+            // and the warps stream through their blocks; one barrier before step 3 (nb >= 6) re-opens the buffers.
+            double* const Ybuf[3] = {Yoth, Wb, Vb};
             for (int s = 0; s < nsteps; ++s) {
+                if (s == 3) __syncthreads();
                 if (warp < nb) {
                     int o = warp + s;
                     if (o >= nb) o -= nb;
@@ -543,12 +549,13 @@ __global__ void __launch_bounds__(32 * NQ, MINB)
                             sbr_symm_block(blk, s == 0, RB0, CB0, tr0, tre, p0, Ub, st, lane, g, t, own, oth);
                         }
                     }
-                    // partner block: add to the shared vector (exclusive during this step)
+                    // partner block: into this step's buffer (no other warp touches the block during the step)
                     if (t < 2) {
+                        double* const yb = Ybuf[s % 3];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            double* y0 = Yoth + (2 * t) * st + 32 * o + 8 * i + g;
-                            if (s == 0) {  // first touch of this block's sums: plain store
+                            double* y0 = yb + (2 * t) * st + 32 * o + 8 * i + g;
+                            if (s < 3) {  // first touch of this block in this buffer: plain store
                                 y0[0] = oth[i][0];
                                 y0[st] = oth[i][1];
                             } else {
@@ -559,9 +566,9 @@ __global__ void __launch_bounds__(32 * NQ, MINB)
                     }
                 }
                 VSP_LAP(2);
-                __syncthreads();
-                VSP_LAP(3);
             }
+            __syncthreads();
+            VSP_LAP(3);
             if (warp < nb && t < 2) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -585,6 +592,8 @@ __global__ void __launch_bounds__(32 * NQ, MINB)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     y[k] = Yoth[k * st + r];
+                    if (nb >= 2) y[k] += Wb[k * st + r];  // partner sums of step 1
+                    if (nb >= 4) y[k] += Vb[k * st + r];  // partner sums of step 2
                     u[k] = Ub[k * st + r];
                 }
 #pragma unroll

@@ -359,11 +359,11 @@ def run_b200_arm(args) -> None:
         v.copy_(a[: lay.arena_elems])
         host_arenas.append(v)
     torch.cuda.synchronize(dev)
-    for _ in range(max(1, args.warmup // 2)):
+    for _ in range(max(1, args.warmup)):
         runner.run_host(host_arenas, want_sv=True)
     sync_all()
     t0 = time.perf_counter()
-    e2e_steps = max(1, args.steps // 2)
+    e2e_steps = max(1, args.steps)
     for _ in range(e2e_steps):
         rec_h, sv_h = runner.run_host(host_arenas, want_sv=True)
     torch.cuda.synchronize(dev)

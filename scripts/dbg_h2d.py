@@ -24,7 +24,7 @@ from vision_spectra_b200.sweep import CheckpointLayout, SweepRunner
 lay = CheckpointLayout.vit(192, 6)
 block = (torch.randn(93 * lay.arena_elems) * 0.02).pin_memory()
 host = [block[i * lay.arena_elems:(i + 1) * lay.arena_elems] for i in range(93)]
-for chunk, lanes in [(12, 4), (6, 6), (8, 6), (6, 8), (12, 4), (6, 6), (8, 6), (6, 8)]:
+for chunk, lanes in [(8, 6), (8, 6), (4, 8), (16, 6)]:
     eng = pkg.SpectraEngine(dev)
     r = SweepRunner(eng, lay, ckpts_per_chunk=chunk, lanes=lanes)
     r.run_host(host); torch.cuda.synchronize()

@@ -43,33 +43,36 @@ VSP_DEV void bidiag_steps(Ctx& ctx, double* X, int ld, int K, int n, int j_begin
             tau = (beta - alpha) / beta;
             vs = 1.0 / (alpha - beta);
         }
-        ctx.sync();  // everyone has read col[j]
         if (ctx.tid == 0) dq[j] = beta;
         if (tau != 0.0) {
             for (int r = j + 1 + ctx.tid; r < K; r += ctx.nthreads) col[r] *= vs;  // v (v_j = 1 implicit)
             ctx.sync();
-            for (int c = j + 1 + ctx.warp; c < n; c += ctx.nwarps) {  // one warp per trailing column
-                double* cc = X + c * ld;
+        }
+        // one warp per trailing column; the pass also collects |X[j, j+2:]|^2 of the updated row j for the
+        // right reflector (one partial per warp), so that row needs no pass and no reduction of its own
+        double s2 = 0.0;
+        for (int c = j + 1 + ctx.warp; c < n; c += ctx.nwarps) {
+            double* cc = X + c * ld;
+            const double cj = cc[j];
+            double w = 0.0;
+            if (tau != 0.0) {
                 double dot = 0.0;
                 for (int r = j + 1 + ctx.lane; r < K; r += ctx.wsize) dot += col[r] * cc[r];
-                const double cj = cc[j];
-                const double w = tau * (ctx.warp_sum(dot) + cj);
+                w = tau * (ctx.warp_sum(dot) + cj);
                 for (int r = j + 1 + ctx.lane; r < K; r += ctx.wsize) cc[r] -= w * col[r];
                 if (ctx.lane == 0) cc[j] = cj - w;
             }
+            if (c >= j + 2) s2 += (cj - w) * (cj - w);
         }
+        if (ctx.lane == 0) part[ctx.warp] = s2;
         ctx.sync();
         // ---- right reflector: annihilate X[j, j+2:n]
         if (j + 1 >= n) {
             if (ctx.tid == 0) eq[j] = 0.0;
             break;
         }
-        double s2 = 0.0;
-        for (int c = j + 2 + ctx.tid; c < n; c += ctx.nthreads) {
-            const double x = X[c * ld + j];
-            s2 += x * x;
-        }
-        const double yn2 = ctx.sum(s2);
+        double yn2 = 0.0;
+        for (int q = 0; q < ctx.nwarps; ++q) yn2 += part[q];
         const double a2 = X[(j + 1) * ld + j];
         double b2 = a2, tau2 = 0.0, us = 0.0;
         if (yn2 > 0.0) {
@@ -81,7 +84,7 @@ VSP_DEV void bidiag_steps(Ctx& ctx, double* X, int ld, int K, int n, int j_begin
         if (tau2 != 0.0) {
             for (int c = j + 1 + ctx.tid; c < n; c += ctx.nthreads)
                 u[c] = (c == j + 1) ? 1.0 : X[c * ld + j] * us;
-            ctx.sync();
+            ctx.sync();  // u complete; every thread has read the warp partials
             // rows j+1..K-1, split into G column groups so that every thread has work
             const int nrows = K - (j + 1), ncols = n - (j + 1);
             int G = ctx.nthreads / (nrows > 0 ? nrows : 1);
@@ -145,30 +148,28 @@ VSP_DEV int gk_singular_values(Ctx& ctx, const double* dq, const double* eq, int
     const int half = (n + 1) >> 1;
     for (int k = ctx.tid; k < half; k += ctx.nthreads) {
         // two singular values per work item (k-th and (k+half)-th smallest); index n + k in the
-        // ascending 2n spectrum; only the non-negative half [0, bound] is searched
+        // ascending 2n spectrum; only the non-negative half [0, bound] is searched, with the same
+        // geometric / counting / interpolating brackets as the Gram route (bisect_metrics.cuh)
         const int kb = k + half;
         const bool has_b = kb < n;
-        double lo_a = 0.0, hi_a = bound, lo_b = 0.0, hi_b = bound;
-        bool done_a = false, done_b = !has_b;
+        Bracket A, B;
+        A.init(0.0, bound, n2, true);
+        B.init(0.0, bound, n2, has_b);
+        A.clo = B.clo = n;  // the Golub-Kahan spectrum is symmetric: n eigenvalues below zero
         int it = 0;
-        for (; it < 200 && !(done_a && done_b); ++it) {
-            const double mid_a = 0.5 * (lo_a + hi_a), mid_b = 0.5 * (lo_b + hi_b);
-            if (!done_a) done_a = (hi_a - lo_a <= fmax(floor_w, 4.440892098500626e-16 * hi_a)) || mid_a <= lo_a || mid_a >= hi_a;
-            if (!done_b) done_b = (hi_b - lo_b <= fmax(floor_w, 4.440892098500626e-16 * hi_b)) || mid_b <= lo_b || mid_b >= hi_b;
-            if (done_a && done_b) break;
-            int na, nb;
-            sturm_count2(de, n2, mid_a, mid_b, na, nb);
-            if (!done_a) {
-                if (na >= n + k + 1) hi_a = mid_a; else lo_a = mid_a;
-            }
-            if (!done_b) {
-                if (nb >= n + kb + 1) hi_b = mid_b; else lo_b = mid_b;
-            }
+        for (; it < 400; ++it) {
+            const double xa = A.next(floor_w), xb = B.next(floor_w);
+            if (A.done && B.done) break;
+            int na, nb, ea, eb;
+            double fa, fb;
+            sturm_count2(de, n2, xa, xb, na, nb, fa, ea, fb, eb);
+            A.update(xa, na, fa, ea, n + k);
+            B.update(xb, nb, fb, eb, n + kb);
         }
-        const double sa = 0.5 * (lo_a + hi_a);
+        const double sa = 0.5 * (A.lo + A.hi);
         lam_out[k] = sa * sa;
         if (has_b) {
-            const double sb = 0.5 * (lo_b + hi_b);
+            const double sb = 0.5 * (B.lo + B.hi);
             lam_out[kb] = sb * sb;
         }
         maxit = it > maxit ? it : maxit;

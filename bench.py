@@ -58,9 +58,9 @@ def load_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r01_traffic.json)."""
     try:
         t = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
-        return {"bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"], "kernel": t["kernel"], "source": t["source"]}
+        return t["dram_bytes_read"] + t["dram_bytes_write"], f'{t["kernel"]}: {t["source"]}' 
     except Exception:
-        return None
+        return None, None
 
 
 def load_peaks() -> dict:
@@ -389,8 +389,9 @@ def run_b200_arm(args) -> None:
     alg = {
         gram_name: {"bound": "hbm", "work": in_bytes / 1e9, "unit": "GB/s", "peak": peaks["hbm_gbs"],
                     "flops": n_ckpt * lay.flops_gram()},
-        eig_name: {"bound": "fp64", "work": n_ckpt * lay.flops_tridiag() / 1e12, "unit": "TFLOP/s", "peak": fp64_peak},
-        "bisect_metrics_kernel": {"bound": "fp64", "work": None, "unit": "TFLOP/s", "peak": fp64_peak},
+        # "tensor": the FP64 tensor cores (DMMA.8x8x4); DMMA and DFMA share the same units and the same measured peak
+        eig_name: {"bound": "tensor", "work": n_ckpt * lay.flops_tridiag() / 1e12, "unit": "TFLOP/s", "peak": fp64_peak},
+        "bisect_metrics_kernel": {"bound": "tensor", "work": None, "unit": "TFLOP/s", "peak": fp64_peak},
     }
     stages = []
     for nm, t in zip(names, stage_ms):
@@ -411,7 +412,8 @@ def run_b200_arm(args) -> None:
         "peak": dom["peak"],
         "unit": dom["unit"],
         "frac": dom["frac"],
-        "traffic": load_traffic(),
+        "traffic": load_traffic()[0],
+        "traffic_source": load_traffic()[1],
         "peak_source": peaks["source"] if dom["bound"] == "hbm" else fp64_src,
         "algorithmic": "4*rows*cols bytes per matrix (hbm) / (4/3) n^3 flops per matrix (fp64 reduction to tridiagonal form); DESIGN.md",
         "hbm_gbs_whole_step": in_bytes / 1e9 / (ms_total / args.steps / 1e3),

@@ -285,10 +285,11 @@ def test_checkpoint_feeder_matches_live_model(engine, tmp_path):
 def test_band_reduction_order_ladder(engine):
     """Stage 2a (sbr_band.cuh + band_tridiag.cuh) at every boundary of its decomposition: orders below one
     panel (n < 6), around the 32-row index blocks, around the launch hand-overs (48, 96, +32), around the
-    shared-memory/L2 split (rows beyond 144 at n > 144) and the one-CTA-per-SM class (192 < n <= 256), square
+    shared-memory/L2 split (rows beyond 144 at n > 144), the one-CTA-per-SM class (192 < n <= 256) and the
+    three-blocks-per-warp class with the matrix in the global workspace (256 < n <= 768), square
     and rectangular, against the oracle's singular values and metrics."""
     orders = [1, 2, 3, 5, 6, 7, 9, 31, 32, 33, 47, 48, 49, 63, 64, 65, 79, 80, 81, 95, 96, 97, 111, 112, 113, 127, 128,
-              129, 143, 144, 145, 159, 160, 161, 176, 191, 192, 193, 208, 224, 255, 256]
+              129, 143, 144, 145, 159, 160, 161, 176, 191, 192, 193, 208, 224, 255, 256, 257, 287, 288, 300, 352, 384, 512, 700]
     rng = np.random.default_rng(2024)
     host = []
     for i, n in enumerate(orders):

@@ -184,24 +184,28 @@ __global__ void __launch_bounds__(32 * kChaseWarps)
 
     // d, e -> workspace (same slots the single-stage kernels fill) and, compacted, to the head of
     // the band buffer for the ill-conditioning gate (one sequential Sturm count by lane 0)
-    double dv[8], ev[8];  // n <= 256
+    // (in chunks of 8 x 32 entries: the compacted copy overwrites band rows that have already been read)
+    for (int i0 = 0; i0 < n; i0 += 256) {
+        double dv[8], ev[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const int i = lane + 32 * t;
-        dv[t] = (i < n) ? L[(size_t)i * kChaseW] : 0.0;
-        ev[t] = (i < n - 1) ? L[(size_t)(i + 1) * kChaseW + 1] : 0.0;
-    }
-    __syncwarp();
+        for (int t = 0; t < 8; ++t) {
+            const int i = i0 + lane + 32 * t;
+            dv[t] = (i < n) ? L[(size_t)i * kChaseW] : 0.0;
+            ev[t] = (i < n - 1) ? L[(size_t)(i + 1) * kChaseW + 1] : 0.0;
+        }
+        __syncwarp();
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const int i = lane + 32 * t;
-        if (i < n) {
-            out[i] = dv[t];
-            out[n + i] = ev[t];
-            L[i] = dv[t];
-            L[n + i] = ev[t];
+        for (int t = 0; t < 8; ++t) {
+            const int i = i0 + lane + 32 * t;
+            if (i < n) {
+                out[i] = dv[t];
+                out[n + i] = ev[t];
+            }
         }
     }
+    __syncwarp();
+    // compact d | e at the head of the (now dead) band buffer, re-read from `out`
+    for (int i = lane; i < 2 * n; i += 32) L[i] = out[i];
     __syncwarp();
     if (lane == 0) {
         int oflags = 0, slot = -1;

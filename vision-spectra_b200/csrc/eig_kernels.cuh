@@ -16,7 +16,8 @@
 
 namespace vsp {
 
-constexpr int kSmemMaxN = 256;  // fused path: 4 chunk pairs of 64 columns; rows beyond 113 KB stay in L2
+constexpr int kSmemMaxN = 768;  // blocked band reduction (packed Gram): one warp per 32-index block up to 256, three
+                                // blocks per warp with the matrix in the global workspace up to 768
 
 __host__ __device__ inline size_t tridiag_global_smem_bytes(int npad) {
     return sizeof(double) * (5 * (size_t)npad + CtaCtx::kScratchDoubles);

@@ -371,7 +371,9 @@ __device__ __forceinline__ void sbr_panel_lq(double* __restrict__ P, double* __r
 }
 
 // NQ = 32-column chunks a lane of the LQ warp holds (= max warps); MINB = CTAs per SM
-template <int NQ, int MINB>
+// BPW = index blocks per warp in the symmetric products (1: the matrix is small enough for one warp per block;
+// 3: orders up to 768 with 8 warps, the matrix in the global workspace throughout)
+template <int NQ, int MINB, int BPW>
 __global__ void __launch_bounds__(32 * NQ, MINB)
     sbr_band_kernel(const ItemDesc* __restrict__ items, int item_base, double* __restrict__ ws, int st, int rows_smem,
                     int m_start, int m_stop) {
@@ -497,7 +499,7 @@ __global__ void __launch_bounds__(32 * NQ, MINB)
         if (warp != 0) {
             if (pending) sbr_update_sweep(A, G, rs_eff, p0, warp - 1, NW - 1, Vb, Wb, st, g, t);
         } else {
-            sbr_panel_lq<(NQ + 1) / 2>(P, Ub, Tm, G, p0, st, lane);
+            sbr_panel_lq<(NQ * BPW + 1) / 2>(P, Ub, Tm, G, p0, st, lane);
             if (NW == 1 && pending) sbr_update_sweep(A, G, rs_eff, p0, 0, 1, Vb, Wb, st, g, t);
         }
         __syncthreads();
@@ -506,27 +508,33 @@ __global__ void __launch_bounds__(32 * NQ, MINB)
         // ---- (3) symmetric products Y = A U over the leading p0 x p0 triangle (cyclic block schedule)
         const int nb = (p0 + 31) >> 5;
         {
-            double own[4][2];  // sums of the own index block, as D fragments: [8-row/col group][kk = 2t, 2t+1]
+            double own[BPW][4][2];  // sums of the own index blocks (warp, warp + NW, ...), as D fragments:
+                                    // [block][8-row/col group][kk = 2t, 2t+1]
 #pragma unroll
-            for (int i = 0; i < 4; ++i) own[i][0] = own[i][1] = 0.0;
+            for (int b = 0; b < BPW; ++b)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) own[b][i][0] = own[b][i][1] = 0.0;
             const int nsteps = (nb >> 1) + 1;
             // The partner sums of step s go to buffer s mod 3: besides Y itself, the buffers of the previous V and W
             // are free from here to the W-phase (the update sweep and the mini-pass were their last readers).  Every
             // step touches every block of its buffer exactly once, so steps 0..2 store, need no barrier between them
-            // and the warps stream through their blocks; one barrier before step 3 (nb >= 6) re-opens the buffers.
+            // and the warps stream through their blocks; a barrier before steps 3, 6, ... re-opens the buffers.
             double* const Ybuf[3] = {Yoth, Wb, Vb};
             for (int s = 0; s < nsteps; ++s) {
-                if (s == 3) __syncthreads();
-                if (warp < nb) {
-                    int o = warp + s;
+                if (s > 0 && s % 3 == 0) __syncthreads();
+#pragma unroll
+                for (int b = 0; b < BPW; ++b) {
+                    const int blk_own = warp + b * NW;
+                    if (blk_own >= nb) continue;  // warp-uniform
+                    int o = blk_own + s;
                     if (o >= nb) o -= nb;
                     const bool half = (2 * s == nb);   // the pair {w, w + nb/2} is met from both sides
-                    const bool own_cols = (s == 0) || (o > warp);
-                    const int rb = own_cols ? o : warp, cb = own_cols ? warp : o;  // stored tile (rb, cb)
+                    const bool own_cols = (s == 0) || (o > blk_own);
+                    const int rb = own_cols ? o : blk_own, cb = own_cols ? blk_own : o;  // stored tile (rb, cb)
                     const int tr0 = (half && !own_cols) ? 2 : 0, tr1 = (half && own_cols) ? 2 : 4;
                     const int RB0 = 32 * rb, CB0 = 32 * cb;
                     // the sums of the own index block accumulate in `own` across the steps, those of the partner
-                    // block in `oth` (added to the shared vector below): own = columns <=> own_cols
+                    // block in `oth` (stored / added to this step's buffer below): own = columns <=> own_cols
                     double oth[4][2];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) oth[i][0] = oth[i][1] = 0.0;
@@ -537,16 +545,16 @@ __global__ void __launch_bounds__(32 * NQ, MINB)
                         if (tre - tr0 > 2 && RB0 + 16 >= rs_eff && RB0 < rs_eff) {
                             // the block straddles the two address spaces: two half blocks
                             if (own_cols) {
-                                sbr_symm_block(A, s == 0, RB0, CB0, tr0, 2, p0, Ub, st, lane, g, t, oth, own);
-                                sbr_symm_block(G, s == 0, RB0, CB0, 2, tre, p0, Ub, st, lane, g, t, oth, own);
+                                sbr_symm_block(A, s == 0, RB0, CB0, tr0, 2, p0, Ub, st, lane, g, t, oth, own[b]);
+                                sbr_symm_block(G, s == 0, RB0, CB0, 2, tre, p0, Ub, st, lane, g, t, oth, own[b]);
                             } else {
-                                sbr_symm_block(A, s == 0, RB0, CB0, tr0, 2, p0, Ub, st, lane, g, t, own, oth);
-                                sbr_symm_block(G, s == 0, RB0, CB0, 2, tre, p0, Ub, st, lane, g, t, own, oth);
+                                sbr_symm_block(A, s == 0, RB0, CB0, tr0, 2, p0, Ub, st, lane, g, t, own[b], oth);
+                                sbr_symm_block(G, s == 0, RB0, CB0, 2, tre, p0, Ub, st, lane, g, t, own[b], oth);
                             }
                         } else if (own_cols) {
-                            sbr_symm_block(blk, s == 0, RB0, CB0, tr0, tre, p0, Ub, st, lane, g, t, oth, own);
+                            sbr_symm_block(blk, s == 0, RB0, CB0, tr0, tre, p0, Ub, st, lane, g, t, oth, own[b]);
                         } else {
-                            sbr_symm_block(blk, s == 0, RB0, CB0, tr0, tre, p0, Ub, st, lane, g, t, own, oth);
+                            sbr_symm_block(blk, s == 0, RB0, CB0, tr0, tre, p0, Ub, st, lane, g, t, own[b], oth);
                         }
                     }
                     // partner block: into this step's buffer (no other warp touches the block during the step)
@@ -569,12 +577,17 @@ __global__ void __launch_bounds__(32 * NQ, MINB)
             }
             __syncthreads();
             VSP_LAP(3);
-            if (warp < nb && t < 2) {
+            if (t < 2) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    double* y0 = Yoth + (2 * t) * st + 32 * warp + 8 * i + g;  // all steps are done: exclusive again
-                    y0[0] += own[i][0];
-                    y0[st] += own[i][1];
+                for (int b = 0; b < BPW; ++b) {
+                    const int blk_own = warp + b * NW;
+                    if (blk_own >= nb) continue;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        double* y0 = Yoth + (2 * t) * st + 32 * blk_own + 8 * i + g;  // all steps are done: exclusive again
+                        y0[0] += own[b][i][0];
+                        y0[st] += own[b][i][1];
+                    }
                 }
             }
         }
@@ -585,27 +598,34 @@ __global__ void __launch_bounds__(32 * NQ, MINB)
             double T[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) T[i] = Tm[i];
-            const int r = tid;
-            double x[4] = {0.0, 0.0, 0.0, 0.0}, u[4] = {0.0, 0.0, 0.0, 0.0};
-            if (r < p0) {
-                double y[4];
+            // thread tid handles the rows tid, tid + nthreads, ... (BPW of them)
+            double x[BPW][4], u[BPW][4], zp[16];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    y[k] = Yoth[k * st + r];
-                    if (nb >= 2) y[k] += Wb[k * st + r];  // partner sums of step 1
-                    if (nb >= 4) y[k] += Vb[k * st + r];  // partner sums of step 2
-                    u[k] = Ub[k * st + r];
+            for (int i = 0; i < 16; ++i) zp[i] = 0.0;
+#pragma unroll
+            for (int q = 0; q < BPW; ++q) {
+                const int r = tid + q * nthreads;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) x[q][k] = u[q][k] = 0.0;
+                if (r < p0) {
+                    double y[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        y[k] = Yoth[k * st + r];
+                        if (nb >= 2) y[k] += Wb[k * st + r];  // partner sums of the steps 1, 4, ...
+                        if (nb >= 4) y[k] += Vb[k * st + r];  // partner sums of the steps 2, 5, ...
+                        u[q][k] = Ub[k * st + r];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int k = 0; k <= j; ++k) x[q][j] = fma(y[k], T[k * 4 + j], x[q][j]);
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int k = 0; k <= j; ++k) x[j] = fma(y[k], T[k * 4 + j], x[j]);
+                    for (int j = 0; j < 4; ++j) zp[i * 4 + j] = fma(u[q][i], x[q][j], zp[i * 4 + j]);
             }
-            double zp[16];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) zp[i * 4 + j] = u[i] * x[j];
             // fold over the 32 lanes: after four levels lane l holds entry (l >> 1), then pair-sum
             double b8[8], b4[4], b2[2], b1;
             {
@@ -646,17 +666,21 @@ __global__ void __launch_bounds__(32 * NQ, MINB)
                     if (k <= i) se = fma(Tm[k * 4 + i], zk, se);
                 }
             }
-            double wv[4] = {x[0], x[1], x[2], x[3]};
+            double sik[16];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 16; ++i) sik[i] = __shfl_sync(0xffffffffu, se, i);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const double sik = __shfl_sync(0xffffffffu, se, 4 * i + k);
-                    wv[k] = fma(-0.5 * u[i], sik, wv[k]);
+            for (int q = 0; q < BPW; ++q) {
+                const int r = tid + q * nthreads;
+                if (r < st) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        double wv = x[q][k];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) wv = fma(-0.5 * u[q][i], sik[4 * i + k], wv);
+                        Wb[k * st + r] = (r < p0) ? wv : 0.0;
+                    }
                 }
-            if (r < st) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) Wb[k * st + r] = (r < p0) ? wv[k] : 0.0;
             }
         }
         // V <- U: swap the two buffers (U is rewritten completely by the next LQ)

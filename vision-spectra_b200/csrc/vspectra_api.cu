@@ -434,7 +434,7 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
                         if (*q == ',') ++q;
                     }
                 } else {
-                    v = {96, 48};
+                    v = {256, 96, 48};
                 }
                 v.push_back(0);
                 return v;
@@ -442,26 +442,29 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
             for (size_t si = 0; si < stops.size(); ++si) {
                 const int order = m_start > 0 ? m_start : c.n;
                 int m_stop = one_launch ? 0 : stops[si];
+                if (order >= 256 + 32 && m_stop < 256) m_stop = one_launch ? 0 : 256;  // the small-order kernels take over below 256
                 if (m_stop > 0 && order < m_stop + 32) continue;  // not worth a launch of its own
-                const int nw = sbr_warps(order);
-                const int stv = 32 * nw;  // stride of the [4][stv] operand arrays
-                switch ((nw + 1) / 2) {
-#define VSP_SBR_CASE(HALF, NQ, MINB)                                                                              \
-    case HALF: {                                                                                                  \
-        const size_t budget = std::min<size_t>(kSbrSmemBudget, (227 * 1024) / MINB - 1024);                       \
-        const int rows_smem = sbr_rows_in_smem(order, stv, nw, budget);                                           \
-        const size_t smem = sbr_smem_bytes(std::min(rows_smem, order), stv, nw);                                  \
-        VSP_CUDA(cudaFuncSetAttribute(sbr_band_kernel<NQ, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                      (int)std::min<size_t>(227 * 1024, std::max<size_t>(budget, 48 * 1024))));   \
-        VSP_CUDA(cudaFuncSetAttribute(sbr_band_kernel<NQ, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,  \
-                                      cudaSharedmemCarveoutMaxShared));                                           \
-        sbr_band_kernel<NQ, MINB><<<c.count, 32 * nw, smem, st>>>(p->d_items, c.begin, ws, stv, rows_smem,        \
-                                                                   m_start, m_stop);                              \
+                const bool big = order > 256;  // three index blocks per warp, matrix mostly in the global workspace
+                const int nw = big ? 8 : sbr_warps(order);
+                const int stv = round_up(order, 32);  // stride of the [4][stv] operand arrays
+                switch (big ? 5 : (nw + 1) / 2) {
+#define VSP_SBR_CASE(HALF, NQ, MINB, BPW)                                                                              \
+    case HALF: {                                                                                                       \
+        const size_t budget = std::min<size_t>(MINB == 1 ? 226 * 1024 : kSbrSmemBudget, (227 * 1024) / MINB - 1024);   \
+        const int rows_smem = sbr_rows_in_smem(order, stv, nw, budget);                                                \
+        const size_t smem = sbr_smem_bytes(std::min(rows_smem, order), stv, nw);                                       \
+        VSP_CUDA(cudaFuncSetAttribute(sbr_band_kernel<NQ, MINB, BPW>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                      (int)std::min<size_t>(227 * 1024, std::max<size_t>(budget, 48 * 1024))));        \
+        VSP_CUDA(cudaFuncSetAttribute(sbr_band_kernel<NQ, MINB, BPW>, cudaFuncAttributePreferredSharedMemoryCarveout,  \
+                                      cudaSharedmemCarveoutMaxShared));                                                \
+        sbr_band_kernel<NQ, MINB, BPW><<<c.count, 32 * nw, smem, st>>>(p->d_items, c.begin, ws, stv, rows_smem,        \
+                                                                        m_start, m_stop);                              \
     } break;
-                    VSP_SBR_CASE(1, 2, 6)
-                    VSP_SBR_CASE(2, 4, 3)
-                    VSP_SBR_CASE(3, 6, 2)
-                    VSP_SBR_CASE(4, 8, 1)
+                    VSP_SBR_CASE(1, 2, 6, 1)
+                    VSP_SBR_CASE(2, 4, 3, 1)
+                    VSP_SBR_CASE(3, 6, 2, 1)
+                    VSP_SBR_CASE(4, 8, 1, 1)
+                    VSP_SBR_CASE(5, 8, 1, 3)
 #undef VSP_SBR_CASE
                     default:
                         return VSP_E_UNSUPPORTED;

@@ -58,7 +58,7 @@ def test_shape_validation_and_layout_queries(lib):
     rows, cols = nat.i32([32, 128, 32, 768]), nat.i32([32, 32, 128, 3072])
     ws = lib.vsp_workspace_bytes(4, nat.p32(rows), nat.p32(cols))
     r1k = lambda v: (v + 1023) // 1024 * 1024
-    f64 = sum(((n * (n + 1) // 2 + (n + 1) // 2 + 3) // 4 * 4 if n <= 256 else n * n) + (2 * n + 4 + 3) // 4 * 4 for n in (32, 32, 32, 768))
+    f64 = sum(((n * (n + 1) // 2 + (n + 1) // 2 + 3) // 4 * 4 if n <= 768 else n * n) + (2 * n + 4 + 3) // 4 * 4 for n in (32, 32, 32, 768))
     i8 = sum(r1k(6 * n * ((k + 63) // 64 * 64)) + r1k(4 * n) for n, k in ((32, 32), (32, 128), (32, 128), (768, 3072)))
     refine = 1024 + sum(r1k(r * c * 8) + 1024 for r, c in ((32, 32), (128, 32), (32, 128), (768, 3072)))
     assert ws == r1k(f64 * 8) + i8 + refine + 2048

@@ -46,7 +46,8 @@ extern "C" int vsp_emul_eig_metrics(const double* gram, int n, int use_full, int
         de[i].e2 = i > 0 ? std::fmax(e[i - 1] * e[i - 1], kE2Floor) : 0.0;
     }
     int next_k = 0;
-    const int iters = bisect_all(ctx, de.data(), n, t, lam.data(), &next_k);
+    std::vector<double> gridbuf(CoarseGrid::doubles(1));
+    const int iters = bisect_all(ctx, de.data(), n, t, lam.data(), &next_k, gridbuf.data());
     MetricOut out = spectral_metrics(ctx, lam.data(), n, scale, flags, fit_start, fit_end, hill_k, sv);
     for (int q = 0; q < 4; ++q) metrics4[q] = out.metrics[q];
     ints6[0] = out.m;

@@ -251,29 +251,111 @@ struct Bracket {
     }
 };
 
+// Coarse grid shared by all brackets of one matrix: G - 1 shifts spaced geometrically over the 44 binary orders
+// of magnitude below the Gershgorin upper bound, evaluated once (two per work item, one Sturm pass) before the
+// brackets start.  An eigenvalue's bracket then starts as one grid cell -- already narrow on the log scale, with
+// counts and det(T - xI) known at both ends -- instead of the whole Gershgorin interval: ~10 Sturm evaluations per
+// eigenvalue instead of ~20.  Layout of `buf` (3 (G + 1) doubles): x[G+1] | f[G+1] | {count, exponent}[G+1].
+struct CoarseGrid {
+    double* x;
+    double* f;
+    int* ce;  // 2 ints per point: count below x, binary exponent of f
+    int G;
+    VSP_DEV static int points(int nthreads) { return 2 * nthreads + 1; }  // G
+    VSP_DEV static int doubles(int nthreads) { return 3 * (points(nthreads) + 1); }
+    VSP_DEV void bind(double* buf, int nthreads) {
+        G = points(nthreads);
+        x = buf;
+        f = buf + (G + 1);
+        ce = reinterpret_cast<int*>(buf + 2 * (G + 1));
+    }
+};
+
 // lam[k], k = 0..n-1 ascending.  Every work item runs two brackets at a time (two independent FP64 chains);
 // a bracket that has converged takes the next eigenvalue index from the shared counter `*next_k` (zeroed by the
 // caller before the call), so that lanes whose eigenvalues converge early keep working instead of idling until
-// the slowest lane of their warp is done.  Returns the number of Sturm evaluations of this work item.
+// the slowest lane of their warp is done.  `gridbuf`: CoarseGrid::doubles(nthreads) doubles of shared scratch.
+// Returns the number of Sturm evaluations of this work item.
 template <class Ctx>
-VSP_DEV int bisect_all(Ctx& ctx, const DE* de, int n, const TriInfo& t, double* lam, int* next_k) {
+VSP_DEV int bisect_all(Ctx& ctx, const DE* de, int n, const TriInfo& t, double* lam, int* next_k, double* gridbuf) {
+    CoarseGrid grid;
+    grid.bind(gridbuf, ctx.nthreads);
+    const int G = grid.G;
+    {   // grid points 1..G-1: x_i = gu * 2^(-44 (G - i) / (G - 1)); 0 and G are the Gershgorin ends
+        const double step = -44.0 / (double)(G - 1);
+        const int ia = 1 + 2 * ctx.tid, ib = 2 + 2 * ctx.tid;
+        const double xa = (t.gu > 0.0) ? t.gu * exp2(step * (double)(G - ia)) : t.gu;
+        const double xb = (t.gu > 0.0 && ib < G) ? t.gu * exp2(step * (double)(G - ib)) : t.gu;
+        int na, nb, ea, eb;
+        double fa, fb;
+        sturm_count2(de, n, xa, xb, na, nb, fa, ea, fb, eb);
+        if (ia < G) {
+            grid.x[ia] = xa;
+            grid.f[ia] = fa;
+            grid.ce[2 * ia] = na;
+            grid.ce[2 * ia + 1] = ea;
+        }
+        if (ib < G) {
+            grid.x[ib] = xb;
+            grid.f[ib] = fb;
+            grid.ce[2 * ib] = nb;
+            grid.ce[2 * ib + 1] = eb;
+        }
+        if (ctx.tid == 0) {
+            grid.x[0] = t.gl;
+            grid.f[0] = 0.0;
+            grid.ce[0] = 0;
+            grid.ce[1] = 0;
+            grid.x[G] = t.gu;
+            grid.f[G] = 0.0;
+            grid.ce[2 * G] = n;
+            grid.ce[2 * G + 1] = 0;
+        }
+    }
+    ctx.sync();
+    // bracket of eigenvalue k = the grid cell [i, i+1] with count(x_i) <= k < count(x_{i+1})
+    auto start = [&](Bracket& br, int k) {
+        br.init(t.gl, t.gu, n, k < n);
+        if (k >= n || !(t.gu > 0.0)) return;
+        int lo = 0, hi = G;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (grid.ce[2 * mid] >= k + 1) hi = mid; else lo = mid;
+        }
+        if (!(grid.x[lo] < grid.x[hi])) return;  // degenerate cell: keep the whole interval
+        br.lo = grid.x[lo];
+        br.hi = grid.x[hi];
+        br.clo = grid.ce[2 * lo];
+        br.chi = grid.ce[2 * hi];
+        br.flo = grid.f[lo];
+        br.fhi = grid.f[hi];
+        br.elo = grid.ce[2 * lo + 1];
+        br.ehi = grid.ce[2 * hi + 1];
+        br.have_lo = lo >= 1;
+        br.have_hi = hi <= G - 1;
+        if (br.lo < t.gl) {  // the cell reaches below the Gershgorin interval (clustered spectra): clip it
+            br.lo = t.gl;
+            br.clo = 0;
+            br.have_lo = false;
+        }
+    };
     int ka = ctx.fetch_add(next_k), kb = ctx.fetch_add(next_k);
     Bracket A, B;
-    A.init(t.gl, t.gu, n, ka < n);
-    B.init(t.gl, t.gu, n, kb < n);
-    int it = 0;
+    start(A, ka);
+    start(B, kb);
+    int it = 1;
     for (; it < 100000; ++it) {
         double xa = A.next(t.atol), xb = B.next(t.atol);
         if (A.done && ka < n) {
             lam[ka] = xa;  // next() returned the midpoint of the collapsed bracket
             ka = ctx.fetch_add(next_k);
-            A.init(t.gl, t.gu, n, ka < n);
+            start(A, ka);
             xa = A.next(t.atol);
         }
         if (B.done && kb < n) {
             lam[kb] = xb;
             kb = ctx.fetch_add(next_k);
-            B.init(t.gl, t.gu, n, kb < n);
+            start(B, kb);
             xb = B.next(t.atol);
         }
         if (ka >= n && kb >= n) break;

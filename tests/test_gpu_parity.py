@@ -344,3 +344,112 @@ def test_repeated_runs_are_bitwise_identical(engine):
         else:
             assert str(rows) == str(ref_rec)
             np.testing.assert_array_equal(sv, ref_sv)
+
+
+def test_resolve_pool_serves_every_flagged_matrix(engine):
+    """More ill-conditioned matrices in one shape class than the FP64 pool has buffers (plan: max(4, count/8)):
+    the re-solve serves the work list in rounds, so every one of them must come back ILLCOND | REFINED and inside
+    the element-wise singular-value gate.  (Round 1 solved the overflow on the Gram route, silently outside it.)"""
+    rng = np.random.default_rng(99)
+    host = []
+    for i in range(48):
+        n = 64
+        u = np.linalg.qr(rng.standard_normal((n, n)))[0]
+        v = np.linalg.qr(rng.standard_normal((n + 8, n)))[0]
+        s = np.logspace(0, -6.0 - (i % 3), n)  # kappa 1e6 .. 1e8
+        host.append(((u * s) @ v.T).astype(np.float64 if i % 2 else np.float32))
+    host += [trunc_normal(rng, (64, 72)) for _ in range(8)]  # well-conditioned ones in the same class
+    metrics, svs, rec = engine.analyze([torch.from_numpy(w).cuda() for w in host])
+    for i, (w, m, s, r) in enumerate(zip(host, metrics, svs, rec)):
+        if i < 48:
+            assert int(r["status"]) & 96 == 96, (i, int(r["status"]))
+        else:
+            assert int(r["status"]) == 0, (i, int(r["status"]))
+        ref_sv = orc.singular_values(w)
+        if w.dtype == np.float32:  # the smallest singular values of the fp32 copy sit at its rounding level
+            nrm, _ = sv_errors(s, ref_sv)
+            assert nrm < SV_RTOL, (i, nrm)
+            keep = ref_sv > 1e-5 * ref_sv[0]
+            assert np.max(np.abs(s[keep] - ref_sv[keep]) / ref_sv[keep]) < SV_RTOL, i
+        else:
+            _check_record(f"pool{i}", w, m, s, r, orc.get_spectral_metrics(w), orc.integer_outputs(w), ref_sv)
+
+
+def test_workspace_bound_covers_every_plan(engine):
+    """vsp_workspace_bytes (shape-only bound of the one-shot entry) is laid out by the same code as a plan: it must
+    cover classes whose items share n but differ wildly in K (the re-solve pool is sized by the largest K*n)."""
+    import ctypes
+
+    from vision_spectra_b200 import _native as nat
+
+    lib = engine.lib
+    for rows, cols in ([[64, 64, 64, 64], [64, 64, 64, 4096]], [[192] * 9 + [768], [192] * 9 + [192]], [[5, 300, 32], [700, 12, 32]]):
+        r, c = nat.i32(rows), nat.i32(cols)
+        bound = lib.vsp_workspace_bytes(len(rows), nat.p32(r), nat.p32(c))
+        for dtype in (nat.VSP_F32, nat.VSP_F64):
+            h = ctypes.c_void_p()
+            nat.check(lib.vsp_plan_create(len(rows), nat.p32(r), nat.p32(c), None, dtype, None, ctypes.byref(h)), "plan")
+            need = lib.vsp_plan_workspace_bytes(h)
+            lib.vsp_plan_destroy(h)
+            assert 0 < need <= bound, (rows, cols, dtype, need, bound)
+
+
+def test_upload_matrices_rebuilds_arbitrary_views(engine):
+    """checkpoint.upload_matrices serves views from one uploaded base: row blocks (the fused qkv case), column
+    blocks and transposed views must all arrive as the SAME values on the device (round 1 reinterpreted the base
+    buffer for non-contiguous views)."""
+    from vision_spectra_b200.checkpoint import upload_matrices
+    from vision_spectra_b200.metrics.extraction import WeightInfo
+
+    g = torch.Generator().manual_seed(3)
+    base = torch.randn(96, 48, generator=g)
+    other = torch.randn(40, 24, generator=g)
+    views = [base[:32], base[32:64], base[:, :16], base[:, 16:48], base.t(), base[10:50, 5:29], other, other.t()[:, ::2]]
+    infos = [WeightInfo(f"v{i}", None, "x", v, tuple(v.shape)) for i, v in enumerate(views)]
+    dev = upload_matrices(infos, torch.device("cuda", 0))
+    torch.cuda.synchronize()
+    for v, d in zip(views, dev):
+        assert tuple(d.weight.shape) == tuple(v.shape)
+        np.testing.assert_array_equal(d.weight.cpu().numpy(), v.numpy())
+    m_dev, _, _ = engine.analyze([d.weight for d in dev], want_sv=False)
+    for v, m in zip(views, m_dev):
+        ref = orc.get_spectral_metrics(v.numpy())
+        for k in orc.METRIC_KEYS:
+            assert metric_close(m[k], ref[k]), (tuple(v.shape), k, m[k], ref[k])
+
+
+def test_integer_and_half_inputs_follow_the_reference_cast(engine):
+    """spectral.py:407 casts every input to float64: integer matrices must be analysed from their exact values
+    (they do not fit fp32 above 2^24), half / bfloat16 from their exactly widened values."""
+    rng = np.random.default_rng(11)
+    wi = rng.integers(-(2**30), 2**30, size=(24, 40)).astype(np.int64)
+    wh = torch.from_numpy(rng.standard_normal((40, 24)).astype(np.float32)).to(torch.bfloat16)
+    wl = rng.standard_normal((16, 16)).astype(np.longdouble)
+    metrics, svs, _ = engine.analyze([wi, wh, wh.cuda(), torch.from_numpy(wi).cuda(), wl])
+    refs = [wi.astype(np.float64), wh.float().numpy(), wh.float().numpy(), wi.astype(np.float64), wl.astype(np.float64)]
+    for m, s, w in zip(metrics, svs, refs):
+        ref = orc.get_spectral_metrics(w)
+        for k in orc.METRIC_KEYS:
+            assert metric_close(m[k], ref[k]), (k, m[k], ref[k])
+        nrm, elem = sv_errors(s, orc.singular_values(w))
+        assert nrm < SV_RTOL and elem < SV_RTOL
+
+
+def test_plans_outlive_cache_eviction():
+    """A SweepRunner keeps the plans of its tables; the engine's LRU cache may evict them (shared engines do:
+    ADVICE r1).  The runner must keep working -- the native plan lives as long as somebody holds the Plan object."""
+    import vision_spectra_b200 as pkg
+    from vision_spectra_b200.sweep import CheckpointLayout, SweepRunner
+
+    eng = pkg.SpectraEngine(torch.device("cuda", 0), max_cached_plans=2)
+    lay = CheckpointLayout.vit(32, 1)
+    runner = SweepRunner(eng, lay, ckpts_per_chunk=2, lanes=1)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    arenas = [torch.randn(lay.arena_elems, generator=g, device="cuda") * 0.02 for _ in range(4)]
+    a = runner.run_device(arenas).records_host()
+    for n in (8, 9, 10, 11, 12):  # five more plans through a two-entry cache
+        eng.analyze([torch.randn(n, n, device="cuda")])
+    b = runner.run_device(arenas).records_host()
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(a["metrics"], b["metrics"])
+    eng.close()

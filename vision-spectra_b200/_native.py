@@ -12,7 +12,10 @@ from pathlib import Path
 
 import numpy as np
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libvspectra.so"
+import os
+
+# VSP_LIB: development override (an alternative build of the same library, e.g. -DVSP_PHASE_TIMING)
+LIB_PATH = Path(os.environ.get("VSP_LIB") or Path(__file__).resolve().parent / "lib" / "libvspectra.so")
 
 VSP_F32, VSP_F64 = 0, 1
 ST_NONFINITE, ST_ZERO, ST_FEW_SV, ST_ALPHA_NAN, ST_HILL_NAN, ST_REFINED, ST_ILLCOND = 1, 2, 4, 8, 16, 32, 64

@@ -124,8 +124,16 @@ def upload_matrices(infos: list[WeightInfo], device: torch.device) -> list[Weigh
     views of it.  fp32 on the device (bf16/fp16 checkpoints widen exactly)."""
     bases: dict[tuple[int, int], tuple[torch.Tensor, int]] = {}  # storage ptr -> (base tensor, arena offset)
     total = 0
-    for wi in infos:
-        base = wi.weight._base if wi.weight._base is not None else wi.weight
+
+    def base_of(w: torch.Tensor) -> torch.Tensor:
+        # a view is served from its base only if the base is laid out densely (then every strided view of it --
+        # row blocks, column blocks, transposes -- can be rebuilt on the device copy); anything else is
+        # uploaded as its own dense matrix
+        b = w._base if w._base is not None else w
+        return b if b.is_contiguous() else w.contiguous()
+
+    resolved = [base_of(wi.weight) for wi in infos]
+    for base in resolved:
         key = (base.untyped_storage().data_ptr(), base.storage_offset())
         if key not in bases:
             bases[key] = (base, total)
@@ -135,16 +143,14 @@ def upload_matrices(infos: list[WeightInfo], device: torch.device) -> list[Weigh
         arena[off : off + base.numel()].copy_(base.detach().reshape(-1).to(torch.float32))
     dev = arena.to(device, non_blocking=True)
     out = []
-    for wi in infos:
-        base = wi.weight._base if wi.weight._base is not None else wi.weight
+    for wi, base in zip(infos, resolved):
         _, off = bases[(base.untyped_storage().data_ptr(), base.storage_offset())]
-        if wi.weight._base is not None and wi.weight.is_contiguous():
-            rel = wi.weight.storage_offset() - base.storage_offset()
-            view = dev[off + rel : off + rel + wi.weight.numel()].view(wi.weight.shape)
+        w = wi.weight
+        if w._base is not None and base is w._base:
+            # same sizes / strides / offset as on the host, relative to the (dense) base: exact for any view
+            view = torch.as_strided(dev, tuple(w.shape), tuple(w.stride()), off + w.storage_offset() - base.storage_offset())
         else:
             view = dev[off : off + base.numel()].view(base.shape)
-            if view.shape != wi.weight.shape:
-                view = view.reshape(wi.weight.shape)
         out.append(WeightInfo(wi.name, wi.layer_idx, wi.matrix_type, view, tuple(view.shape)))
     return out
 

@@ -210,11 +210,9 @@ __global__ void __launch_bounds__(32 * kChaseWarps)
     if (lane == 0) {
         int oflags = 0, slot = -1;
         if (gate.counter != nullptr && has_tiny_eigenvalue(L, L + n, n)) {  // kappa >~ 3e4: re-solve from W
-            slot = atomicAdd(gate.counter, 1);
-            if (slot < gate.slots) {
-                oflags = VSP_ST_ILLCOND;
-                gate.slot_items[slot] = item_base + idx;
-            }
+            slot = atomicAdd(gate.counter, 1);  // list entry (the list holds every item of the class)
+            oflags = VSP_ST_ILLCOND;
+            gate.slot_items[slot] = item_base + idx;
         }
         out[2 * n + MISC_FLAGS] = (double)oflags;
         out[2 * n + MISC_SLOT] = (double)slot;

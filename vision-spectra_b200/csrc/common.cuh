@@ -71,12 +71,14 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
 // misc[] slots written by the tridiagonalisation stage
 enum { MISC_SCALE = 0, MISC_FLAGS = 1, MISC_SLOT = 2, MISC_UNUSED1 = 3, MISC_COUNT = 4 };
 
-// Claim ticket for the ill-conditioned re-solve: the tridiagonalisation kernels test the small
-// end of the spectrum with one Sturm count and, if it is populated, take a slot of the FP64 pool.
+// Work list of the ill-conditioned re-solve: the tridiagonalisation kernels test the small end of
+// the spectrum with one Sturm count and, if it is populated, append the item to the list.  The list
+// has one entry per item of the shape class, so it cannot overflow; the FP64 pool only bounds how
+// many entries are re-solved at the same time (refine_kernel: CTA b serves entries b, b + slots, ...).
 struct RefineGate {
     int* counter;     // zeroed by the host before every execution; nullptr = re-solve disabled
-    int* slot_items;  // slot -> position of the claiming item in the plan's item table
-    int slots;
+    int* slot_items;  // list entry -> position of the flagged item in the plan's item table
+    int slots;        // pool buffers = CTAs of the re-solve launch
 };
 
 #if !defined(__CUDACC__)

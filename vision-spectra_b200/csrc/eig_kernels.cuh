@@ -75,11 +75,9 @@ __global__ void tridiag_global_kernel(const ItemDesc* __restrict__ items, int it
     if (ctx.tid == 0) {
         int oflags = 0, slot = -1;
         if (gate.counter != nullptr && has_tiny_eigenvalue(d, e, n)) {
-            slot = atomicAdd(gate.counter, 1);
-            if (slot < gate.slots) {
-                oflags = VSP_ST_ILLCOND;
-                gate.slot_items[slot] = item_base + blockIdx.x;
-            }
+            slot = atomicAdd(gate.counter, 1);  // list entry (the list holds every item of the class)
+            oflags = VSP_ST_ILLCOND;
+            gate.slot_items[slot] = item_base + blockIdx.x;
         }
         out[2 * n + MISC_SCALE] = scale;
         out[2 * n + MISC_FLAGS] = (double)oflags;
@@ -149,8 +147,8 @@ __global__ void __launch_bounds__(MAXT, MINB) bisect_metrics_kernel(const ItemDe
 
 // ------------------------------------------------------------------------------------------
 // Re-solve of the matrices the tridiagonalisation flagged VSP_ST_ILLCOND (refine_bidiag.cuh).
-// One CTA per pool slot: CTA s serves the item that claimed slot s (slots are handed out in
-// increasing order, so the working CTAs are scheduled first and the rest exit at once).
+// One CTA per pool buffer: CTA b serves the list entries b, b + slots, b + 2 slots, ... with its own FP64
+// buffer, so any number of flagged items is re-solved (in rounds when there are more than `slots`).
 struct RefinePool {
     double* base;        // slots x slot_doubles
     int slots;
@@ -167,8 +165,9 @@ __global__ void __launch_bounds__(1024)
                   vsp_opts opts, double* __restrict__ sv_out, vsp_record* __restrict__ records) {
     extern __shared__ __align__(16) double smem[];
     const int slot = blockIdx.x;
-    if (slot >= *gate.counter) return;  // unclaimed slot
-    const ItemDesc it = items[gate.slot_items[slot]];
+    const int nflagged = *gate.counter;
+    for (int entry = slot; entry < nflagged; entry += pool.slots) {
+    const ItemDesc it = items[gate.slot_items[entry]];
     const int n = it.n, K = it.kdim;
     double* red = smem;
     double* dq = red + CtaCtx::kScratchDoubles;
@@ -240,6 +239,8 @@ __global__ void __launch_bounds__(1024)
         r.metrics[2] = mo.metrics[2];
         r.metrics[3] = mo.metrics[3];
         records[it.item] = r;
+    }
+    ctx.sync();  // the next entry reuses the shared scratch and the pool buffer
     }
 }
 

@@ -8,7 +8,7 @@
 //   sum_k q_ik q_jk = sum_{s} 128^(10-s) P_s[i][j],   P_s = sum_{t+t'=s} S_t S_t'^T.
 //
 // Every P_s is an int8 x int8 -> int32 tensor-core product (tcgen05.mma kind::i8): exact, no
-// rounding anywhere (|P_s| <= 6 * 4096 * 64^2 < 2^27).  Levels s = 0..6 (26 digit pairs) are
+// rounding anywhere (|P_s| <= 6 K 64^2: < 2^27 for K <= 4096, < 2^31 up to the route's limit kI8MaxK).  Levels s = 0..6 (26 digit pairs) are
 // kept: the dropped ones are below 2^-46 of the result, i.e. the Gram matrix is as accurate as
 // the FP64-accumulated one (5e-15 measured) and the 1e-5 singular-value gate survives the
 // squaring of the condition number (plain 3xTF32 does not).
@@ -30,7 +30,6 @@
 
 #include <cuda.h>
 
-#include "common.cuh"
 #include "common.cuh"  // poff()
 
 namespace vsp {
@@ -44,6 +43,9 @@ constexpr int kI8Stages = 3;
 constexpr int kI8StageBytes = kDigits * (kI8TileM + kI8TileN) * kI8ChunkK;  // 73728
 constexpr int kI8SmemBytes = kI8Stages * kI8StageBytes + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int kI8MaxTiles = 64;
+// Longest contraction the int8 route takes: |P_s| <= 6 K 64^2 must stay below 2^31 (K < 87 381) and the low Horner
+// half P3 128^3 + ... + P6 below 2^53; 65 536 leaves a factor of 1.3.  Longer K: FP64 Gram kernel (vspectra_api.cu).
+constexpr int kI8MaxK = 65536;
 
 // Gram class: all items of a plan with the same (n, Kp); they share one digit-plane tensor.
 struct I8Class {

@@ -37,6 +37,42 @@ inline bool cuda_ok(cudaError_t e, const char* what) {
         if (!cuda_ok((call), #call)) return VSP_E_CUDA; \
     } while (0)
 
+// Development aid (VSP_KERNEL_TIMING=1): one CUDA event after every launch of an execution, per-launch times
+// printed to stderr after a stream synchronisation.  Off by default: no events, no synchronisation.
+struct LaunchTimer {
+    bool on = false;
+    std::vector<std::pair<std::string, cudaEvent_t>> ev;
+    void start(cudaStream_t st) {
+        static const bool enabled = std::getenv("VSP_KERNEL_TIMING") != nullptr;
+        on = enabled;
+        tick("begin", st);
+    }
+    void tick(const char* name, cudaStream_t st) {
+        if (!on) return;
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        cudaEventRecord(e, st);
+        ev.emplace_back(name, e);
+    }
+    void report(cudaStream_t st) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        for (auto& pe : ev) cudaEventSynchronize(pe.second);
+        std::string line = "[vsp timing]";
+        for (size_t i = 1; i < ev.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second);
+            char buf[96];
+            std::snprintf(buf, sizeof buf, " %s=%.3f", ev[i].first.c_str(), ms);
+            line += buf;
+        }
+        std::fprintf(stderr, "%s\n", line.c_str());
+        for (auto& pe : ev) cudaEventDestroy(pe.second);
+        ev.clear();
+    }
+};
+thread_local LaunchTimer t_timer;
+
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 inline int64_t round_up64(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
@@ -132,6 +168,7 @@ int launch_gram_i8(const vsp_plan* p, const ShapeClass& c, double* ws, unsigned 
         dim3 sgrid(g.count, (g.n + 31) / 32);
         slice_i8_kernel<<<sgrid, 256, 0, st>>>(p->d_items, g, wsb);
         g_launches++;
+        t_timer.tick("slice_i8", st);
         if (!cuda_ok(cudaGetLastError(), "slice_i8_kernel")) return VSP_E_CUDA;
         CUtensorMap tmA, tmB;
         int rc = make_plane_map(&tmA, wsb + g.slice_off, g, kI8TileM);
@@ -143,6 +180,7 @@ int launch_gram_i8(const vsp_plan* p, const ShapeClass& c, double* ws, unsigned 
         dim3 mgrid(g.mtiles, g.count);
         gram_i8_mma_kernel<<<mgrid, 192, kI8SmemBytes, st>>>(p->d_items, g, wsb, ws, tmA, tmB);
         g_launches++;
+        t_timer.tick("gram_i8_mma", st);
         if (!cuda_ok(cudaGetLastError(), "gram_i8_mma_kernel")) return VSP_E_CUDA;
     }
     return VSP_OK;
@@ -203,33 +241,24 @@ static int64_t item_ws_doubles(int n, int full) {
     return round_up64(gram, 4) + round_up64(2 * (int64_t)n + MISC_COUNT, 4);
 }
 
+static int plan_layout(vsp_plan* p, int32_t count, const int32_t* rows, const int32_t* cols, const int64_t* ld,
+                       int32_t dtype, const vsp_opts* opts);
+static int64_t plan_total_bytes(const vsp_plan* plan);
+
+// Upper bound for any plan over these shapes: the layout of the fp32 plan (the fp64 plan has the same FP64 and
+// re-solve regions and no digit planes), computed by the same code that lays out a real plan.
 int64_t vsp_workspace_bytes(int32_t count, const int32_t* rows, const int32_t* cols) {
     const int rc = validate(count, rows, cols, nullptr);
     if (rc != VSP_OK) return rc;
-    int64_t total = 0, i8 = 0;
-    for (int i = 0; i < count; ++i) {
-        const int n = std::min(rows[i], cols[i]);
-        total += item_ws_doubles(n, n > kSmemMaxN);
-        // fp32 inputs: six int8 digit planes [n][Kp] + row exponents (upper bound: per-item rounding)
-        i8 += round_up64((int64_t)kDigits * n * round_up(std::max(rows[i], cols[i]), kI8ChunkK), 1024) +
-              round_up64((int64_t)n * 4, 1024);
-    }
-    // re-solve pools: at most one slot per item (plans use count/8 slots per shape class)
-    int64_t refine = 1024;
-    for (int i = 0; i < count; ++i)
-        refine += round_up64((int64_t)rows[i] * cols[i] * 8, 1024) + 1024;
-    return round_up64(total * (int64_t)sizeof(double), 1024) + i8 + refine + 2048;
+    vsp_plan tmp;
+    const int lrc = plan_layout(&tmp, count, rows, cols, nullptr, VSP_F32, nullptr);
+    if (lrc != VSP_OK) return lrc;
+    return plan_total_bytes(&tmp) + 256;  // + alignment slack inside the caller's buffer
 }
 
-int vsp_plan_create(int32_t count, const int32_t* rows, const int32_t* cols, const int64_t* ld, int32_t dtype,
-                    const vsp_opts* opts, vsp_plan** out_plan) {
-    if (!out_plan) return VSP_E_ARG;
-    *out_plan = nullptr;
-    if (dtype != VSP_F32 && dtype != VSP_F64) return VSP_E_UNSUPPORTED;
-    const int rc = validate(count, rows, cols, ld);
-    if (rc != VSP_OK) return rc;
-    vsp_plan* p = new (std::nothrow) vsp_plan();
-    if (!p) return VSP_E_ALLOC;
+// host-side part of a plan: shape classes, workspace layout (no CUDA calls)
+static int plan_layout(vsp_plan* p, int32_t count, const int32_t* rows, const int32_t* cols, const int64_t* ld,
+                       int32_t dtype, const vsp_opts* opts) {
     p->count = count;
     p->dtype = dtype;
     if (opts) {
@@ -288,6 +317,10 @@ int vsp_plan_create(int32_t count, const int32_t* rows, const int32_t* cols, con
         const char* e = std::getenv("VSP_GRAM");
         p->gram_method = (e && std::string(e) == "f64") ? 0 : 1;
     }
+    // The exactness argument of the int8 split (gram_i8.cuh: every level sum fits int32, the Horner halves fit
+    // 2^53) holds for contraction lengths up to kI8MaxK; a plan with a longer one takes the FP64 Gram kernel.
+    for (int s = 0; s < count; ++s)
+        if (p->items[s].kdim > kI8MaxK) p->gram_method = 0;
     if (dtype == VSP_F32 && p->gram_method == 1) {
         int64_t boff = 0;
         for (int s = 0; s < count; ++s) {
@@ -329,14 +362,33 @@ int vsp_plan_create(int32_t count, const int32_t* rows, const int32_t* cols, con
             for (int s = c.begin; s < c.begin + c.count; ++s)
                 kn = std::max<int64_t>(kn, (int64_t)p->items[s].kdim * p->items[s].n);
             c.refine_slot_doubles = round_up64(kn, 4);
-            c.refine_slots = std::min(c.count, std::max(4, c.count / 8));
+            // pool buffers = CTAs of the re-solve launch (1024 threads: one per SM); more flagged items than
+            // buffers are served in rounds, so the pool never limits how many items can be re-solved
+            c.refine_slots = std::min(c.count, std::max(4, std::min(c.count / 8, 2 * 148)));
             c.refine_counter = idx++;
-            c.refine_items_off = roff;  // slot -> item table
-            roff += round_up64((int64_t)c.refine_slots * 4, 1024);
+            c.refine_items_off = roff;  // work list: one entry per item of the class
+            roff += round_up64((int64_t)c.count * 4, 1024);
             c.refine_off = roff;
             roff += round_up64(c.refine_slot_doubles * 8 * c.refine_slots, 1024);
         }
         p->refine_bytes = roff;
+    }
+    return VSP_OK;
+}
+
+int vsp_plan_create(int32_t count, const int32_t* rows, const int32_t* cols, const int64_t* ld, int32_t dtype,
+                    const vsp_opts* opts, vsp_plan** out_plan) {
+    if (!out_plan) return VSP_E_ARG;
+    *out_plan = nullptr;
+    if (dtype != VSP_F32 && dtype != VSP_F64) return VSP_E_UNSUPPORTED;
+    const int rc = validate(count, rows, cols, ld);
+    if (rc != VSP_OK) return rc;
+    vsp_plan* p = new (std::nothrow) vsp_plan();
+    if (!p) return VSP_E_ALLOC;
+    const int lrc = plan_layout(p, count, rows, cols, ld, dtype, opts);
+    if (lrc != VSP_OK) {
+        delete p;
+        return lrc;
     }
     if (count > 0) {
         if (!cuda_ok(cudaGetDevice(&p->device), "cudaGetDevice") ||
@@ -353,10 +405,11 @@ int vsp_plan_create(int32_t count, const int32_t* rows, const int32_t* cols, con
 }
 
 static int64_t plan_f64_bytes(const vsp_plan* plan) { return round_up64(plan->ws_doubles * (int64_t)sizeof(double), 1024); }
-
-int64_t vsp_plan_workspace_bytes(const vsp_plan* plan) {
-    return plan ? plan_f64_bytes(plan) + plan->i8_bytes + plan->refine_bytes + 2048 : VSP_E_ARG;
+static int64_t plan_total_bytes(const vsp_plan* plan) {
+    return plan_f64_bytes(plan) + plan->i8_bytes + plan->refine_bytes + 2048;
 }
+
+int64_t vsp_plan_workspace_bytes(const vsp_plan* plan) { return plan ? plan_total_bytes(plan) : VSP_E_ARG; }
 int64_t vsp_plan_sv_count(const vsp_plan* plan) { return plan ? plan->sv_total : VSP_E_ARG; }
 
 void vsp_plan_destroy(vsp_plan* plan) {
@@ -391,6 +444,7 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
     }
     VSP_CUDA(cudaMemcpyAsync(p->d_items, p->items.data(), sizeof(ItemDesc) * (size_t)p->count,
                              cudaMemcpyHostToDevice, st));
+    t_timer.start(st);
 
     // per-device attribute; cheap enough to set on every call (one process may drive several GPUs)
     VSP_CUDA(cudaFuncSetAttribute(tridiag_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -446,7 +500,12 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
                 if (m_stop > 0 && order < m_stop + 32) continue;  // not worth a launch of its own
                 const bool big = order > 256;  // three index blocks per warp, matrix mostly in the global workspace
                 const int nw = big ? 8 : sbr_warps(order);
-                const int stv = round_up(order, 32);  // stride of the [4][stv] operand arrays
+                // stride of the [4][stv] operand arrays: = 4 mod 8 doubles, so that the four k-rows of a DMMA operand
+                // fragment (addresses t * stv + g) fall into four different 32-byte bank groups.  With stv a
+                // multiple of 32 they all hit the same one (4-way conflict on every operand load): measured
+                // 4.97 -> 4.63 ms on the first order range of the Scenario-A sweep.
+                static const int stpad = std::getenv("VSP_SBR_STPAD") ? std::atoi(std::getenv("VSP_SBR_STPAD")) : 4;
+                const int stv = round_up(order, 32) + stpad;
                 switch (big ? 5 : (nw + 1) / 2) {
 #define VSP_SBR_CASE(HALF, NQ, MINB, BPW)                                                                              \
     case HALF: {                                                                                                       \
@@ -470,6 +529,7 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
                         return VSP_E_UNSUPPORTED;
                 }
                 g_launches++;
+                t_timer.tick("sbr_band", st);
                 VSP_CUDA(cudaGetLastError());
                 if (m_stop == 0) break;
                 m_start = order - 4 * ((order - m_stop + 3) / 4);  // the order the launch stopped at
@@ -485,6 +545,7 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
                                                                                               ws, c.npad, gate);
         }
         g_launches++;
+        t_timer.tick("chase/tridiag", st);
         VSP_CUDA(cudaGetLastError());
         if ((rc = mark()) != VSP_OK) return rc;
         // The re-solve of the items the tridiagonalisation flagged runs beside the bisection kernel.
@@ -511,6 +572,7 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
                 refine_kernel<double><<<c.refine_slots, 1024, rsm, st>>>(p->d_items, gate, pool, c.npad, xs_doubles, p->opts, d_sv, d_records);
             }
             g_launches++;
+            t_timer.tick("refine", st);
             VSP_CUDA(cudaGetLastError());
             bst = p->side;
         }
@@ -522,6 +584,7 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
             bisect_metrics_kernel<1024, 1><<<c.count, bthreads, bisect_smem_bytes(c.npad), bst>>>(p->d_items, c.begin, ws, c.npad,
                                                                                                   p->opts, d_sv, d_records);
         g_launches++;
+        t_timer.tick("bisect", bst);
         VSP_CUDA(cudaGetLastError());
         if (fork) {  // join
             VSP_CUDA(cudaEventRecord(p->ev_join, p->side));
@@ -529,6 +592,8 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
         }
         if ((rc = mark()) != VSP_OK) return rc;
     }
+    t_timer.tick("joined", st);
+    t_timer.report(st);
     return VSP_OK;
 }
 

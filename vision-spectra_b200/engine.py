@@ -49,6 +49,34 @@ class BatchResult:
         return None if self.sv is None else self.sv.cpu().numpy()
 
 
+class Plan:
+    """Owner of one native `vsp_plan` (validated, device-resident shape table of a batch).
+
+    The engine's LRU cache and every caller that keeps a plan (`SweepRunner`) hold references to this object;
+    the native plan is destroyed when the last reference goes away, after the device has finished with its item
+    table.  A plan must not be executed on two streams at the same time (the native side rewrites the item
+    pointers and shares one fork/join event pair per plan): `SweepRunner` keeps one plan per compute lane."""
+
+    __slots__ = ("handle", "_lib", "_device", "__weakref__")
+
+    def __init__(self, lib, handle: int, device: torch.device):
+        self._lib, self.handle, self._device = lib, handle, device
+
+    def close(self) -> None:
+        h, self.handle = self.handle, None
+        if h is not None:
+            try:
+                torch.cuda.synchronize(self._device)  # kernels may still read the item table
+            finally:
+                self._lib.vsp_plan_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class SpectraEngine:
     """Owns the per-device scratch (workspace, result buffers, cached plans)."""
 
@@ -63,14 +91,14 @@ class SpectraEngine:
             raise nat.NativeError(f"SpectraEngine needs a CUDA device, got {self.device}")
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
-        self._plans: OrderedDict[tuple, int] = OrderedDict()
+        self._plans: OrderedDict[tuple, Plan] = OrderedDict()
         self._max_plans = max_cached_plans
         self._ws: torch.Tensor | None = None
         self._pinned: torch.Tensor | None = None
         self._pinned_busy: torch.cuda.Event | None = None
 
     # ------------------------------------------------------------------ plans
-    def _plan(self, rows, cols, ld, dtype: int, opts: nat.VspOpts) -> int:
+    def _plan(self, rows, cols, ld, dtype: int, opts: nat.VspOpts) -> Plan:
         key = (rows.tobytes(), cols.tobytes(), ld.tobytes(), dtype, opts.fit_start, opts.fit_end, opts.hill_k, opts.want_sv, opts.refine)
         plan = self._plans.get(key)
         if plan is not None:
@@ -82,19 +110,14 @@ class SpectraEngine:
                 self.lib.vsp_plan_create(len(rows), nat.p32(rows), nat.p32(cols), nat.p64(ld), dtype, ctypes.byref(opts), ctypes.byref(handle)),
                 "vsp_plan_create",
             )
-        self._plans[key] = handle.value
+        plan = self._plans[key] = Plan(self.lib, handle.value, self.device)
         while len(self._plans) > self._max_plans:
-            _, old = self._plans.popitem(last=False)
-            torch.cuda.synchronize(self.device)  # kernels may still read the old item table
-            self.lib.vsp_plan_destroy(old)
-        return handle.value
+            self._plans.popitem(last=False)  # destroyed when its last holder (e.g. a SweepRunner) lets go
+        return plan
 
     def close(self) -> None:
-        if self._plans:
-            torch.cuda.synchronize(self.device)
-            for plan in self._plans.values():
-                self.lib.vsp_plan_destroy(plan)
-            self._plans.clear()
+        """Drop the cached plans (each is destroyed once nobody else holds it)."""
+        self._plans.clear()
 
     def __del__(self):
         try:
@@ -144,7 +167,7 @@ class SpectraEngine:
         fit_range: tuple[int, int] | None = None,
         hill_k: int | None = None,
         want_sv: bool = True,
-        plan: int | None = None,
+        plan: Plan | None = None,
         stage_ms: list | None = None,
         out_records: torch.Tensor | None = None,
         out_sv: torch.Tensor | None = None,
@@ -157,8 +180,10 @@ class SpectraEngine:
         ptrs = np.ascontiguousarray(ptrs, dtype=np.uint64)
         if plan is None:
             plan = self.make_plan(rows, cols, ld, dtype, fit_range, hill_k, want_sv)
-        ws_bytes = self.lib.vsp_plan_workspace_bytes(plan)
-        sv_count = self.lib.vsp_plan_sv_count(plan)
+        if plan.handle is None:
+            raise nat.NativeError("analyze_raw: the plan has been closed")
+        ws_bytes = self.lib.vsp_plan_workspace_bytes(plan.handle)
+        sv_count = self.lib.vsp_plan_sv_count(plan.handle)
         if self._ws is None or self._ws.numel() < ws_bytes:
             self._ws = None
             self._ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=self.device)
@@ -169,7 +194,7 @@ class SpectraEngine:
             raise ValueError("analyze_raw: output buffers do not match the batch")
         stream = torch.cuda.current_stream(self.device).cuda_stream
         args = (
-            plan,
+            plan.handle,
             ptrs.ctypes.data_as(ctypes.POINTER(ctypes.c_void_p)),
             None if sv is None else sv.data_ptr(),
             records.data_ptr(),
@@ -188,8 +213,9 @@ class SpectraEngine:
         np.cumsum(np.minimum(rows, cols), out=offs[1:])
         return BatchResult(records, sv, offs, count)
 
-    def make_plan(self, rows, cols, ld, dtype: int, fit_range=None, hill_k=None, want_sv: bool = True) -> int:
-        """Validated, device-resident shape table for a batch (cached per engine)."""
+    def make_plan(self, rows, cols, ld, dtype: int, fit_range=None, hill_k=None, want_sv: bool = True) -> Plan:
+        """Validated, device-resident shape table for a batch (cached per engine; the returned `Plan` stays
+        valid for as long as the caller holds it, whatever the cache evicts)."""
         opts = nat.VspOpts.make(fit_range, hill_k, want_sv)
         return self._plan(nat.i32(rows), nat.i32(cols), nat.i64(ld), dtype, opts)
 
@@ -232,8 +258,9 @@ class SpectraEngine:
         (non-2-D input, empty matrix, NaN/Inf entries) yields NaN metrics and
         `None` singular values; nothing raises for bad *data*.
 
-        float64 inputs are analysed from their float64 values, everything else is
-        widened/narrowed to float32 first (model weights are fp32/bf16/fp16)."""
+        float32 / float16 / bfloat16 inputs are analysed from their (exactly widened) float32 values; float64,
+        integer and extended-precision inputs from float64, as the reference's `np.asarray(w, dtype=np.float64)`
+        sees them (spectral.py:407)."""
         count = len(matrices)
         metrics: list[dict[str, float]] = [nan_metrics() for _ in range(count)]
         svs: list[np.ndarray | None] = [None] * count
@@ -253,19 +280,22 @@ class SpectraEngine:
                     if w.device != self.device:
                         w = w.to(self.device)
                     if w.dtype not in (torch.float32, torch.float64):
-                        w = w.float()
+                        w = w.float() if w.dtype in (torch.float16, torch.bfloat16) else w.double()
                     if (w.shape[1] > 1 and w.stride(1) != 1) or (w.shape[0] > 1 and w.stride(0) < w.shape[1]):
                         w = w.contiguous()
                     groups[w.dtype].append((i, w))
                     continue
-                w = w.float().numpy() if w.dtype not in (torch.float32, torch.float64) else w.numpy()
+                if w.dtype not in (torch.float32, torch.float64):
+                    w = w.float() if w.dtype in (torch.float16, torch.bfloat16) else w.double()
+                w = w.numpy()
             else:
                 w = np.asarray(w)
                 if w.dtype.kind not in "fiub":
                     continue
             if w.ndim != 2 or w.size == 0:
                 continue
-            npdt = np.float64 if w.dtype == np.float64 else np.float32
+            # half / single precision widen exactly to fp32; ints and long doubles go to float64 like the reference
+            npdt = np.float32 if (w.dtype.kind == "f" and w.dtype.itemsize <= 4) else np.float64
             host[npdt].append((i, w))
         for npdt, lst in host.items():
             if lst:

@@ -13,6 +13,8 @@
 #include "refine_bidiag.cuh"
 #include "tridiag.cuh"
 #include "sbr_band.cuh"
+#include "sbr8.cuh"
+#include "chase8.cuh"
 
 namespace vsp {
 

@@ -236,9 +236,13 @@ int vsp_sv_offsets(int32_t count, const int32_t* rows, const int32_t* cols, int6
     return VSP_OK;
 }
 
-static int64_t item_ws_doubles(int n, int full) {
-    const int64_t gram = full ? (int64_t)n * n : poff(n);
-    return round_up64(gram, 4) + round_up64(2 * (int64_t)n + MISC_COUNT, 4);
+// doubles of one item's Gram region: the packed triangle (or the full matrix) and, for the orders the bandwidth-8
+// reduction takes (sbr8.cuh), its compact band output behind it
+static int64_t item_gram_doubles(int n, int full) {
+    if (full) return round_up64((int64_t)n * n, 4);
+    int64_t g = round_up64(poff(n), 4);
+    if (sbr8_order(n) <= kSbr8MaxN) g += round_up64(sbr8_band_doubles(n), 4);
+    return g;
 }
 
 static int plan_layout(vsp_plan* p, int32_t count, const int32_t* rows, const int32_t* cols, const int64_t* ld,
@@ -295,9 +299,8 @@ static int plan_layout(vsp_plan* p, int32_t count, const int32_t* rows, const in
         it.item = i;
         it.full = it.n > kSmemMaxN ? 1 : 0;
         it.sv_off = sv_off[i];
-        const int64_t gram = it.full ? (int64_t)it.n * it.n : poff(it.n);
         it.gram_off = off;
-        off += round_up64(gram, 4);
+        off += item_gram_doubles(it.n, it.full);
         it.de_off = off;
         off += round_up64(2 * (int64_t)it.n + MISC_COUNT, 4);
         if (p->classes.empty() || p->classes.back().n != it.n) {
@@ -473,7 +476,42 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
             gate.slot_items = reinterpret_cast<int*>(refine_base + c.refine_items_off);
             gate.slots = c.refine_slots;
         }
-        if (!c.full) {
+        static const bool use_sbr8 = std::getenv("VSP_NO_SBR8") == nullptr;  // experiments: round-1 kernels
+        if (!c.full && use_sbr8 && sbr8_order(c.n) <= kSbr8MaxN) {
+            // two-stage reduction, bandwidth 8, matrix resident in shared memory (sbr8.cuh, chase8.cuh).  One launch
+            // per order range: > 136 twelve warps / one CTA per SM, > 72 eight warps / two, else four warps / up to six.
+            const int N = sbr8_order(c.n);
+            int m_start = 0;
+            for (;;) {
+                const int order = m_start > 0 ? m_start : N;
+                const int stv = sbr8_stride(order);
+                int m_stop = order > 136 ? 128 : (order > 72 ? 64 : 0);
+                static const bool one_launch8 = std::getenv("VSP_SBR8_ONE_LAUNCH") != nullptr;  // experiments
+                if (one_launch8) m_stop = 0;
+#define VSP_SBR8_LAUNCH(NW, MINB, NC, TB)                                                                               \
+    {                                                                                                                   \
+        const size_t smem = sbr8_smem_bytes(order, stv, NW);                                                            \
+        VSP_CUDA(cudaFuncSetAttribute(sbr8_kernel<NW, MINB, NC, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                      (int)std::max<size_t>(smem, 48 * 1024)));                                         \
+        VSP_CUDA(cudaFuncSetAttribute(sbr8_kernel<NW, MINB, NC, TB>, cudaFuncAttributePreferredSharedMemoryCarveout,    \
+                                      cudaSharedmemCarveoutMaxShared));                                                 \
+        sbr8_kernel<NW, MINB, NC, TB><<<c.count, 32 * NW, smem, st>>>(p->d_items, c.begin, ws, stv, m_start, m_stop);   \
+    }
+                if (order > 136) VSP_SBR8_LAUNCH(12, 1, 6, 2)
+                else if (order > 72) VSP_SBR8_LAUNCH(8, 2, 4, 2)
+                else VSP_SBR8_LAUNCH(4, 4, 2, 2)
+#undef VSP_SBR8_LAUNCH
+                g_launches++;
+                t_timer.tick("sbr8", st);
+                VSP_CUDA(cudaGetLastError());
+                if (m_stop == 0) break;
+                m_start = m_stop;
+            }
+            const size_t csm = chase8_smem_bytes(c.n);
+            VSP_CUDA(cudaFuncSetAttribute(chase8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)std::max<size_t>(csm, 48 * 1024)));
+            chase8_kernel<<<c.count, kChase8Threads, csm, st>>>(p->d_items, c.begin, c.count, ws, gate);
+        } else if (!c.full) {
             // two-stage reduction: blocked Householder to bandwidth 4 (sbr_band.cuh), bulge chasing (band_tridiag.cuh).
             // The blocked stage is launched per order range (n -> 96 -> 48 -> end): a smaller active block means a
             // smaller CTA, so more matrices share an SM while the steps are latency-bound.

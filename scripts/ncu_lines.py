@@ -24,6 +24,10 @@ for ln in dis.split("\n"):
     if m and cur: line_of[int(m.group(1), 16)] = cur
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
+sel = sys.argv[5] if len(sys.argv) > 5 else None  # substring of the demangled kernel name (several kernels match the regex)
+if sel:
+    k0 = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and sel in r[1]][0]
+    rows = rows[k0:]
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 h = rows[hi]
 ia, iex, isamp = h.index("Address"), h.index("Instructions Executed"), h.index("# Samples")
@@ -31,6 +35,7 @@ stall_cols = [i for i, x in enumerate(h) if x.startswith("stall_") and "Not Issu
 agg = defaultdict(lambda: [0, 0, Counter()])
 base = None; tot_s = tot_e = 0
 for r in rows[hi + 1:]:
+    if r and r[0] == "Kernel Name": break  # the next kernel of a multi-kernel match
     try: a = int(r[ia], 16)
     except Exception: continue
     if base is None: base = a

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(kChase8Threads)
     // entry of the previous tick while everybody writes this tick's, so one barrier per tick is enough
     int* prog = reinterpret_cast<int*>(L + (size_t)rows * kChase8W);
     double* out = ws + it.de_off;
-    const double* __restrict__ Bd = ws + it.gram_off + ((poff(n) + 3) & ~3);
+    const double* __restrict__ Bd = ws + it.gram_off + sbr8_band_off(n);
 
     if (out[2 * n + MISC_FLAGS] != 0.0) return;  // non-finite / all-zero: stage 2a-1 wrote d = e = 0 (uniform over the CTA)
 

@@ -36,17 +36,45 @@ struct ItemDesc {
     int32_t kdim;      // max(rows, cols): contraction length
     int32_t trans;     // 1: Gram = W^T W (rows > cols), 0: Gram = W W^T
     int32_t item;      // index in the caller's batch
-    int32_t full;      // 1: Gram stored full n*n (global-memory eigensolve), 0: packed lower
+    int32_t full;      // Gram layout: kGramPacked (row-packed lower), kGramFull (n*n), kGramTiled (8x8 tiles, sbr8.cuh)
     int32_t pad;
 };
 
 VSP_HD int64_t tri(int64_t i) { return (i * (i + 1)) >> 1; }
+
+enum { kGramPacked = 0, kGramFull = 1, kGramTiled = 2 };
+
+// kGramTiled: the matrix sits at the bottom-right of an N x N frame, N = round_up(n, 8) (off = N - n zero rows / columns
+// at the top-left); lower triangle of 8 x 8 tiles, tile (I, J), J <= I, at (I (I + 1) / 2 + J) * 64 doubles, row-major
+// inside the tile (= the DMMA C-fragment order); diagonal tiles hold both triangles.
+VSP_HD int tile_off(int I, int J) { return (((I * (I + 1)) >> 1) + J) << 6; }
 
 // offset of row r in the padded-even packed lower triangle: row r starts at tri(r) + (r+1)/2, i.e. rows are
 // padded to an even length so that every row starts 16-byte aligned (the Gram kernels write this layout)
 VSP_HD int poff(int r) { return ((r * (r + 1)) >> 1) + ((r + 1) >> 1); }
 
 #if defined(__CUDACC__)
+// store G[i][j] (j <= i) of an n x n Gram matrix in the item's layout (the Gram kernels' epilogues)
+__device__ __forceinline__ void gram_store(double* __restrict__ G, int layout, int n, int i, int j, double g) {
+    if (layout == kGramFull) {
+        G[(int64_t)i * n + j] = g;
+        G[(int64_t)j * n + i] = g;
+    } else if (layout == kGramTiled) {
+        const int off = ((n + 7) & ~7) - n;
+        const int fi = i + off, fj = j + off;
+        const int base = tile_off(fi >> 3, fj >> 3);
+        G[base + ((fi & 7) << 3) + (fj & 7)] = g;
+        if ((fi >> 3) == (fj >> 3) && i != j) G[base + ((fj & 7) << 3) + (fi & 7)] = g;  // diagonal tile: mirror
+        if (off > 0 && j == 0) {  // zero the frame padding once: columns < off of this row, and the rows < off (by row 0)
+            for (int c = 0; c < off; ++c) G[tile_off(fi >> 3, 0) + ((fi & 7) << 3) + c] = 0.0;
+            if (i == 0)
+                for (int e = 0; e < 8 * off; ++e) G[e] = 0.0;
+        }
+    } else {
+        G[poff(i) + j] = g;
+    }
+}
+
 __device__ __forceinline__ double shfl_xor_d(double v, int mask) { return __shfl_xor_sync(0xffffffffu, v, mask); }
 
 // 1/x and 1/sqrt(x) for normal positive doubles: hardware seed + two Newton steps

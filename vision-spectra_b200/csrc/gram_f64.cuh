@@ -9,8 +9,7 @@
 // buffer (pointer + ld), no copies (reference split: metrics/extraction.py:59-62).
 #pragma once
 
-#include "common.cuh"
-#include "common.cuh"  // poff()
+#include "common.cuh"  // gram_store()
 
 namespace vsp {
 
@@ -96,14 +95,7 @@ __global__ void __launch_bounds__(256) gram_f64_kernel(const ItemDesc* __restric
 #pragma unroll
         for (int c = 0; c < RT; ++c) {
             const int j = j0 + tx + 16 * c;
-            if (i < n && j <= i) {
-                if (it.full) {
-                    G[(int64_t)i * n + j] = acc[r][c];
-                    G[(int64_t)j * n + i] = acc[r][c];
-                } else {
-                    G[poff(i) + j] = acc[r][c];  // padded-even packed rows (common.cuh: poff)
-                }
-            }
+            if (i < n && j <= i) gram_store(G, it.full, n, i, j, acc[r][c]);
         }
     }
 }

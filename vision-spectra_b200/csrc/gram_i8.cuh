@@ -342,6 +342,16 @@ __global__ void __launch_bounds__(192, 1)
         const int* __restrict__ E = reinterpret_cast<const int*>(wsb + cls.exp_off) + (int64_t)item * n;
         const int Ei = (i < n) ? E[i] : 1;
         double* __restrict__ G = ws + it.gram_off;
+        // kGramTiled (sbr8.cuh): frame coordinates and the offsets that only depend on this thread's row
+        const int layout = it.full;
+        const int foff = ((n + 7) & ~7) - n, fi = i + foff, fI = fi >> 3;
+        const int frow = tile_off(fI, 0) + ((fi & 7) << 3);    // + 64 * tile column + column in tile
+        const int fdiag = tile_off(fI, fI) + (fi & 7);         // mirror inside the diagonal tile: + 8 * column in tile
+        if (layout == kGramTiled && foff > 0 && i < n) {       // the frame padding is zero
+            for (int c = 0; c < foff; ++c) G[frow + c] = 0.0;
+            if (i == 0)
+                for (int e = 0; e < 8 * foff; ++e) G[e] = 0.0;
+        }
         for (int ti = 0; ti < ntiles; ++ti) {
             const int nt = ti;
             mbar_wait(accbar, ti & 1);
@@ -404,7 +414,11 @@ __global__ void __launch_bounds__(192, 1)
                                 const int be = Ei + Ej - 306 + 1023;
                                 g = acc[k] * __hiloint2double(be << 20, 0);
                             }
-                            if (it.full) {
+                            if (layout == kGramTiled) {
+                                const int fj = j + foff;
+                                G[frow + ((fj >> 3) << 6) + (fj & 7)] = g;
+                                if ((fj >> 3) == fI) G[fdiag + ((fj & 7) << 3)] = g;  // diagonal tile: both triangles
+                            } else if (layout == kGramFull) {
                                 G[(int64_t)i * n + j] = g;
                                 G[(int64_t)j * n + i] = g;
                             } else {

@@ -238,11 +238,18 @@ int vsp_sv_offsets(int32_t count, const int32_t* rows, const int32_t* cols, int6
 
 // doubles of one item's Gram region: the packed triangle (or the full matrix) and, for the orders the bandwidth-8
 // reduction takes (sbr8.cuh), its compact band output behind it
-static int64_t item_gram_doubles(int n, int full) {
-    if (full) return round_up64((int64_t)n * n, 4);
-    int64_t g = round_up64(poff(n), 4);
-    if (sbr8_order(n) <= kSbr8MaxN) g += round_up64(sbr8_band_doubles(n), 4);
-    return g;
+static bool use_sbr8() {
+    static const bool on = std::getenv("VSP_NO_SBR8") == nullptr;  // experiments: round-1 kernels for every order
+    return on;
+}
+static int gram_layout(int n) {
+    if (n > kSmemMaxN) return kGramFull;
+    return (use_sbr8() && sbr8_order(n) <= kSbr8MaxN) ? kGramTiled : kGramPacked;
+}
+static int64_t item_gram_doubles(int n, int layout) {
+    if (layout == kGramFull) return round_up64((int64_t)n * n, 4);
+    if (layout == kGramTiled) return sbr8_band_off(n) + round_up64(sbr8_band_doubles(n), 4);
+    return round_up64(poff(n), 4);
 }
 
 static int plan_layout(vsp_plan* p, int32_t count, const int32_t* rows, const int32_t* cols, const int64_t* ld,
@@ -297,7 +304,7 @@ static int plan_layout(vsp_plan* p, int32_t count, const int32_t* rows, const in
         it.kdim = std::max(rows[i], cols[i]);
         it.trans = rows[i] > cols[i] ? 1 : 0;
         it.item = i;
-        it.full = it.n > kSmemMaxN ? 1 : 0;
+        it.full = gram_layout(it.n);
         it.sv_off = sv_off[i];
         it.gram_off = off;
         off += item_gram_doubles(it.n, it.full);
@@ -310,7 +317,7 @@ static int plan_layout(vsp_plan* p, int32_t count, const int32_t* rows, const in
             c.begin = s;
             c.count = 0;
             c.npad = round_up(it.n, 32);
-            c.split = c.full ? 1 : std::max(1, std::min(4, 384 / c.npad));
+            c.split = c.full == kGramFull ? 1 : std::max(1, std::min(4, 384 / c.npad));
             p->classes.push_back(c);
         }
         p->classes.back().count++;
@@ -476,8 +483,7 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
             gate.slot_items = reinterpret_cast<int*>(refine_base + c.refine_items_off);
             gate.slots = c.refine_slots;
         }
-        static const bool use_sbr8 = std::getenv("VSP_NO_SBR8") == nullptr;  // experiments: round-1 kernels
-        if (!c.full && use_sbr8 && sbr8_order(c.n) <= kSbr8MaxN) {
+        if (c.full == kGramTiled) {
             // two-stage reduction, bandwidth 8, matrix resident in shared memory (sbr8.cuh, chase8.cuh).  One launch
             // per order range: > 136 twelve warps / one CTA per SM, > 72 eight warps / two, else four warps / up to six.
             const int N = sbr8_order(c.n);
@@ -511,7 +517,7 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
             VSP_CUDA(cudaFuncSetAttribute(chase8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)std::max<size_t>(csm, 48 * 1024)));
             chase8_kernel<<<c.count, kChase8Threads, csm, st>>>(p->d_items, c.begin, c.count, ws, gate);
-        } else if (!c.full) {
+        } else if (c.full == kGramPacked) {
             // two-stage reduction: blocked Householder to bandwidth 4 (sbr_band.cuh), bulge chasing (band_tridiag.cuh).
             // The blocked stage is launched per order range (n -> 96 -> 48 -> end): a smaller active block means a
             // smaller CTA, so more matrices share an SM while the steps are latency-bound.
@@ -645,7 +651,14 @@ __global__ void expand_gram_kernel(const ItemDesc* __restrict__ items, const dou
     for (int64_t e = threadIdx.x; e < (int64_t)n * n; e += blockDim.x) {
         const int i = (int)(e / n), j = (int)(e % n);
         const int r = i > j ? i : j, c = i > j ? j : i;
-        o[e] = it.full ? G[(int64_t)r * n + c] : G[poff(r) + c];
+        if (it.full == kGramFull) {
+            o[e] = G[(int64_t)r * n + c];
+        } else if (it.full == kGramTiled) {
+            const int off = sbr8_order(n) - n, fr = r + off, fc = c + off;
+            o[e] = G[tile_off(fr >> 3, fc >> 3) + ((fr & 7) << 3) + (fc & 7)];
+        } else {
+            o[e] = G[poff(r) + c];
+        }
     }
 }
 

@@ -38,8 +38,16 @@ __host__ __device__ inline size_t chase8_smem_bytes(int n) {
     return sizeof(double) * ((size_t)(n + kChase8PadRows) * kChase8W + 4 * kChase8Groups);
 }
 
-// sum of eight values as a tree (three dependent additions instead of seven)
-__host__ __device__ inline double tree8(const double (&a)[8]) { return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7])); }
+// dot product of two 8-vectors as two chains of four (half the dependent latency of one chain, one more instruction)
+__host__ __device__ inline double dot8(const double (&a)[8], const double (&b)[8]) {
+    double s0 = a[0] * b[0], s1 = a[1] * b[1];
+#pragma unroll
+    for (int i = 2; i < 8; i += 2) {
+        s0 = fma(a[i], b[i], s0);
+        s1 = fma(a[i + 1], b[i + 1], s1);
+    }
+    return s0 + s1;
+}
 
 #if defined(__CUDACC__)
 
@@ -86,8 +94,11 @@ __global__ void __launch_bounds__(kChase8Threads)
             ready = (k == 0) || (ap == 0) || (kp > k - 1) || (kp == k - 1 && jp >= j + kChase8Lag);
         }
         par ^= 1;
-        if (ready) {  // uniform over the eight lanes of a group
-            const int r0 = k + 1 + 8 * j;
+        // Every lane runs the step body, converged: groups that are not ready work on row 0 and store nothing.  (With
+        // the body under `if (ready)` the eight-lane exchange became a sub-warp shuffle in divergent code, which
+        // the compiler lowers to a WARPSYNC.COLLECTIVE loop.)
+        {
+            const int r0 = ready ? k + 1 + 8 * j : 0;
             const int xj = (j == 0) ? 1 : 8;  // jj of x_0: column r0-1 (first step) or r0-8
             double* Lr = L + (size_t)r0 * kChase8W;
             double x[8];
@@ -98,85 +109,80 @@ __global__ void __launch_bounds__(kChase8Threads)
 #pragma unroll
             for (int c = 0; c < 8; ++c) dq[c] = (c <= q) ? Lr[q * kChase8W + q - c] : Lr[c * kChase8W + c - q];
             // (a) column q of the left block, (c) row q of the lower block
+            // (columns left of the matrix, ca < 0, read band slots beyond the row start: zero and never written)
             const int ca = r0 - 8 + q;
             double a[8], cc[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = (ca >= 0) ? Lr[i * kChase8W + 8 + i - q] : 0.0;
+            for (int i = 0; i < 8; ++i) a[i] = Lr[i * kChase8W + 8 + i - q];
             double* Lc = Lr + (size_t)(8 + q) * kChase8W;  // row r0 + 8 + q
 #pragma unroll
             for (int c = 0; c < 8; ++c) cc[c] = Lc[8 + q - c];
-            __syncwarp(gmask);  // the group's loads precede its stores (other groups work on other rows)
-            double sq[8];
-            sq[0] = 0.0;
+            const double xq = Lr[q * kChase8W + xj + q];  // x_q: this lane's entry of the reflector
+            __syncwarp();  // a group's loads precede its stores (other groups work on other rows)
+            double xn2;
+            {
+                double s0 = x[1] * x[1], s1 = x[2] * x[2];
+                s0 = fma(x[3], x[3], s0);
+                s1 = fma(x[4], x[4], s1);
+                s0 = fma(x[5], x[5], s0);
+                s1 = fma(x[6], x[6], s1);
+                xn2 = fma(x[7], x[7], s0) + s1;
+            }
+            const bool doit = ready && xn2 > 0.0;
+            double beta, tau, vs;
+            const double s2 = fma(x[0], x[0], xn2);
+            {
+                const double rs = fast_rsqrt(s2);
+                const double nrm = s2 * rs;
+                beta = -copysign(nrm, x[0]);
+                tau = fma(fabs(x[0]), rs, 1.0);
+                vs = copysign(fast_rcp(fabs(x[0]) + nrm), x[0]);
+            }
+            if (doit && !(s2 > 1e-280)) {  // sub-normal range: exact division (never taken after the power-of-four scaling)
+                beta = -copysign(sqrt(s2), x[0]);
+                tau = (beta - x[0]) / beta;
+                vs = 1.0 / (x[0] - beta);
+            }
+            double v[8];
+            v[0] = 1.0;
 #pragma unroll
-            for (int i = 1; i < 8; ++i) sq[i] = x[i] * x[i];
-            const double xn2 = tree8(sq);
-            if (xn2 > 0.0) {
-                double beta, tau, vs;
-                const double s2 = fma(x[0], x[0], xn2);
-                if (s2 > 1e-280) {
-                    const double rs = fast_rsqrt(s2);
-                    const double nrm = s2 * rs;
-                    beta = -copysign(nrm, x[0]);
-                    tau = fma(fabs(x[0]), rs, 1.0);
-                    vs = copysign(fast_rcp(fabs(x[0]) + nrm), x[0]);
-                } else {
-                    beta = -copysign(sqrt(s2), x[0]);
-                    tau = (beta - x[0]) / beta;
-                    vs = 1.0 / (x[0] - beta);
-                }
-                double v[8];
-                v[0] = 1.0;
+            for (int i = 1; i < 8; ++i) v[i] = x[i] * vs;
+            // (b): p = tau D v (lane q: entry q), exchanged inside the group
+            const double pq = tau * dot8(dq, v);
+            double p[8];
 #pragma unroll
-                for (int i = 1; i < 8; ++i) v[i] = x[i] * vs;
-                // (b): p = tau D v (lane q: entry q), exchanged inside the group
-                double pr[8];
+            for (int c = 0; c < 8; ++c) p[c] = __shfl_sync(0xffffffffu, pq, c, 8);
+            const double K = 0.5 * tau * dot8(v, p);
+            const double vq = (q == 0) ? 1.0 : xq * vs;  // v_q, w_q of this lane without register indexing
+            const double wq = fma(-K, vq, pq);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) pr[c] = dq[c] * v[c];
-                const double pq = tau * tree8(pr);
-                double p[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) p[c] = __shfl_sync(gmask, pq, c, 8);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) pr[c] = v[c] * p[c];
-                const double K = 0.5 * tau * tree8(pr);
-                double vq = 0.0, wq = 0.0;  // v_q, w_q of this lane (static indexing only)
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    p[c] = fma(-K, v[c], p[c]);  // w
-                    if (c == q) {
-                        vq = v[c];
-                        wq = p[c];
-                    }
-                }
+            for (int c = 0; c < 8; ++c) p[c] = fma(-K, v[c], p[c]);  // w
+            if (doit) {
 #pragma unroll
                 for (int c = 0; c < 8; ++c)
                     if (c <= q) Lr[q * kChase8W + q - c] = dq[c] - fma(vq, p[c], wq * v[c]);
-                // (a)
-                if (ca >= 0) {
-                    if (8 - q == xj) {  // the column the reflector was built from
-                        a[0] = beta;
+            }
+            // (a)
+            {
+                const double ts = tau * dot8(a, v);
+                const bool src = (8 - q == xj);  // the column the reflector was built from
 #pragma unroll
-                        for (int i = 1; i < 8; ++i) a[i] = 0.0;
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) pr[i] = a[i] * v[i];
-                        const double ts = tau * tree8(pr);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) a[i] = fma(-ts, v[i], a[i]);
-                    }
+                for (int i = 0; i < 8; ++i) a[i] = src ? (i == 0 ? beta : 0.0) : fma(-ts, v[i], a[i]);
+                if (doit && ca >= 0) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) Lr[i * kChase8W + 8 + i - q] = a[i];
                 }
-                // (c)
-                {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) pr[c] = cc[c] * v[c];
-                    const double ts = tau * tree8(pr);
+            }
+            // (c)
+            {
+                const double ts = tau * dot8(cc, v);
+                if (doit) {
 #pragma unroll
                     for (int c = 0; c < 8; ++c) Lc[8 + q - c] = fma(-ts, v[c], cc[c]);
                 }
             }
+        }
+        if (ready) {
             ++j;
             if (k + 1 + 8 * j > n - 2) {
                 k += kChase8Groups;

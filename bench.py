@@ -54,10 +54,29 @@ def measure_fp64_peak():
     return FP64_PEAK_TFLOPS, "derived: 148 SM x 64 FP64 FMA/clk x 1.965 GHz (no FP64 figure in MEASURED_PEAKS.json)"
 
 
+def measure_i8_peak():
+    """int8 tensor-core peak of this GPU (tcgen05.mma kind::i8), measured live with scripts/micro/i8_umma_bench.cu:
+    (TOPS at the production shape M=128 N=64 K=32, TOPS at N=256, source).  Falls back to 2x the measured bf16
+    figure of MEASURED_PEAKS.json, said so in the source string."""
+    import subprocess
+
+    exe = ROOT / "vision-spectra_b200" / "lib" / "i8_umma_bench"
+    try:
+        out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60).stdout
+        vals = {ln.split(":")[0].strip(): float(ln.split(":")[1].split()[0]) for ln in out.splitlines() if ln.startswith("i8 umma")}
+        if "i8 umma m128n64k32" in vals and "i8 umma m128n256k32" in vals:
+            return vals["i8 umma m128n64k32"], vals["i8 umma m128n256k32"], "measured live: tcgen05.mma kind::i8 issue-loop microbenchmark, scripts/micro/i8_umma_bench.cu"
+    except Exception:
+        pass
+    d = load_peaks()
+    return 2.0 * d["bf16_tflops"], 2.0 * d["bf16_tflops"], "derived: 2 x bf16 burst of " + d["source"] + " (microbenchmark did not run)"
+
+
 def load_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r01_traffic.json)."""
     try:
-        t = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
+        cand = sorted((ROOT / "profiles").glob("r*_traffic.json"))
+        t = json.loads(cand[-1].read_text())
         return t["dram_bytes_read"] + t["dram_bytes_write"], f'{t["kernel"]}: {t["source"]}' 
     except Exception:
         return None, None
@@ -158,8 +177,31 @@ def _cpu_worker_init():
     _blas_limit = threadpool_limits(1)
 
 
+_ref_mod = None
+
+
+def reference_kind() -> str:
+    """"reference": oracle/_ref holds the reference's own metrics/spectral.py (oracle/build_ref.py); "port": it does
+    not, the oracle restatement is timed instead."""
+    return "reference" if (ROOT / "oracle" / "_ref" / "ref_spectral.py").exists() else "port"
+
+
 def _cpu_worker(w):
+    """One matrix the way the reference's driver treats it (experiments/run_spectral_analysis.py:323-336):
+    get_spectral_metrics (4 SVDs) + the fifth SVD that stores the singular values."""
+    global _ref_mod
     sys.path.insert(0, str(ROOT / "oracle"))
+    if reference_kind() == "reference":
+        if _ref_mod is None:
+            import build_ref
+
+            _ref_mod = build_ref.load_ref()
+        import numpy as np
+        from scipy.linalg import svd
+
+        m = _ref_mod.get_spectral_metrics(w)
+        svd(np.asarray(w, dtype=np.float64), compute_uv=False)
+        return m["stable_rank"]
     import spectral_oracle as orc
 
     out = orc.reference_cost_metrics(w)  # 4 metric SVDs + the driver's 5th SVD
@@ -210,9 +252,9 @@ def host_cores() -> int:
 
 
 def run_reference_arm(args) -> None:
-    """`--impl reference`: the reference's own CPU algorithm for this path.  The reference
-    is pure Python over SciPy (nothing to compile into oracle/_ref), so this times the
-    oracle port -- same SciPy/LAPACK calls, 5 SVDs per matrix -- on all host cores."""
+    """`--impl reference`: the reference's own CPU implementation of this path on all host cores: the reference's
+    metrics/spectral.py itself when oracle/_ref has been built (oracle/build_ref.py, `kind: "reference"`), else the
+    oracle port (same SciPy/LAPACK calls, `kind: "port"`); 5 SVDs per matrix either way."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -250,11 +292,236 @@ def run_reference_arm(args) -> None:
         "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": SCENARIO["name"], "matrices_per_step": len(mats), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "matrices/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "matrices/s", "cores": cores, "kind": reference_kind(), "sample": sample},
         "e2e": {"value": value, "unit": "matrices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+
+# ------------------------------------------------------------- extras (outside the headline timed region)
+SCENARIOS = {  # reference table experiments/run_spectral_analysis.py:145-236: (embed_dim, depth, epochs incl. epoch 0)
+    "A": (192, 6, 31), "B": (192, 6, 51), "C": (96, 3, 51), "D": (96, 3, 31), "E": (32, 1, 31), "F": (32, 1, 51),
+}
+SEEDS = (42, 142, 242)  # run_spectral_analysis.py:706
+
+
+def _device_time(fn, sync_all, steps: int, warmup: int = 2) -> float:
+    """ms per call of fn(), CUDA events on the current stream, barrier + synchronize on both sides, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    for _ in range(warmup):
+        fn()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda", dtype=torch.float64)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def extra_six_scenario_sweep(eng, dev, world: int, rank: int, sync_all, steps: int = 3) -> dict:
+    """BASELINE.json configs[3]: the full six-scenario x 3-seed x every-epoch sweep (14 760 matrices in three shape
+    classes), STRONG-scaled: the 738 checkpoints are dealt to the ranks by longest-processing-time
+    (sweep.partition_lpt on the per-checkpoint cost), every rank analyses its shard in ONE batched call and rank 0
+    receives one ragged gather of 64-byte records."""
+    import numpy as np
+    import torch
+
+    from vision_spectra_b200 import _native as nat
+    from vision_spectra_b200.sweep import CheckpointLayout, gather_records_ragged, matrix_cost, partition_lpt
+
+    layouts = {k: CheckpointLayout.vit(d, depth) for k, (d, depth, _) in SCENARIOS.items()}
+    ckpts = [(k, seed, ep) for k, (_, _, epochs) in SCENARIOS.items() for seed in SEEDS for ep in range(epochs)]
+    costs = [sum(matrix_cost(sl.rows, sl.cols) for sl in layouts[k].slots) for k, _, _ in ckpts]
+    shard = partition_lpt(costs, world)[rank]
+    arenas, ptrs, rows, cols = [], [], [], []
+    for ci in shard:
+        k, seed, ep = ckpts[ci]
+        lay = layouts[k]
+        g = torch.Generator(device=dev).manual_seed(seed * 1_000_003 + ep * 7 + ord(k))
+        a = torch.randn(lay.arena_elems, generator=g, device=dev, dtype=torch.float32) * 0.02
+        arenas.append(a)
+        base = np.uint64(a.data_ptr())
+        ptrs.append(base + np.array([4 * sl.offset for sl in lay.slots], dtype=np.uint64))
+        rows.append(np.array([sl.rows for sl in lay.slots], np.int32))
+        cols.append(np.array([sl.cols for sl in lay.slots], np.int32))
+    ptrs, rows, cols = np.concatenate(ptrs), np.concatenate(rows), np.concatenate(cols)
+    ld = cols.astype(np.int64)
+    plan = eng.make_plan(rows, cols, ld, nat.VSP_F32, want_sv=True)
+    state = {}
+
+    def step():
+        res = eng.analyze_raw(ptrs, rows, cols, ld, nat.VSP_F32, want_sv=True, plan=plan)
+        state["res"] = res
+        state["gathered"] = gather_records_ragged(res.records) if world > 1 else res.records
+
+    ms = _device_time(step, sync_all, steps)
+    rec = state["res"].records_host()
+    ok = bool(((rec["status"] == 0) | (rec["status"] == 96)).all())
+    total = sum(len(layouts[k].slots) for k, _, _ in ckpts)
+    if rank == 0 and world > 1:
+        assert state["gathered"].numel() == total * 64, "ragged gather lost records"
+    del arenas
+    return {"workload": "six scenarios x 3 seeds x every epoch (A,D,E 31 ckpts; B,C,F 51 ckpts)", "matrices": total,
+            "checkpoints": len(ckpts), "scaling": "strong", "n_gpus": world, "ms": ms, "matrices_per_s": total / (ms / 1e3),
+            "shard_matrices_rank0": int(len(ptrs)), "records_clean": ok,
+            "partition": "sweep.partition_lpt over checkpoints; gather_records_ragged of 64-byte records"}
+
+
+def extra_scenario(eng, dev, key: str, sync_all, steps: int = 3) -> dict:
+    """One scenario's sweep (every epoch x 3 seeds), device-resident, on this rank (BASELINE.json configs[0] / [2])."""
+    import torch
+
+    from vision_spectra_b200.sweep import CheckpointLayout, SweepRunner
+
+    d, depth, epochs = SCENARIOS[key]
+    lay = CheckpointLayout.vit(d, depth)
+    runner = SweepRunner(eng, lay)
+    g = torch.Generator(device=dev).manual_seed(1000 + ord(key))
+    arenas = [torch.randn(lay.arena_elems, generator=g, device=dev, dtype=torch.float32) * 0.02 for _ in range(epochs * len(SEEDS))]
+    ms = _device_time(lambda: runner.run_device(arenas, want_sv=True), sync_all, steps)
+    n = len(arenas) * lay.matrices
+    return {"workload": f"Scenario {key}: ViT {d}d/{depth}L, {epochs} epochs x {len(SEEDS)} seeds", "matrices": n, "ms": ms,
+            "matrices_per_s": n / (ms / 1e3), "per_rank": True}
+
+
+def extra_vit_base_stress(eng, dev, sync_all, ckpts: int = 16, chunk: int = 4) -> dict:
+    """BASELINE.json configs[4]: ViT-Base 768d/12L random-init checkpoints (72 matrices each, up to 768x3072), analysed
+    in chunks of `chunk` checkpoints (1.36 GB of inputs per chunk, regenerated per chunk: 10 000 checkpoints would be
+    3.4 TB).  Reports matrices/s of this rank and the stage times / FP64 roofline of the n = 768 reduction."""
+    import torch
+
+    from vision_spectra_b200.sweep import CheckpointLayout, SweepRunner
+
+    lay = CheckpointLayout.vit(768, 12)
+    runner = SweepRunner(eng, lay)
+    g = torch.Generator(device=dev).manual_seed(768)
+    arenas = [torch.randn(lay.arena_elems, generator=g, device=dev, dtype=torch.float32) * 0.02 for _ in range(chunk)]
+    runner.run_device(arenas, want_sv=True)  # warm-up (plan, workspace)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    refined = 0
+    e0.record()
+    for c in range(0, ckpts, chunk):
+        for a in arenas:  # the next chunk's checkpoints (device-side generation is part of the chunk loop, not of the metric)
+            a.normal_(0.0, 0.02, generator=g)
+        res = runner.run_device(arenas, want_sv=True)
+        refined += int((res.records_host()["status"] == 96).sum())
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    sm: list = []
+    runner.run_device(arenas, want_sv=True, stage_ms=sm)
+    sync_all()
+    n = ckpts * lay.matrices
+    flops = chunk * lay.flops_tridiag()
+    return {"workload": f"ViT-Base 768d/12L, {ckpts} checkpoints in chunks of {chunk}", "matrices": n, "ms": ms,
+            "matrices_per_s": n / (ms / 1e3), "refined": refined, "per_rank": True,
+            "stage_ms_per_chunk": {"gram": sm[0], "reduction": sm[1], "bisect_refine": sm[2]},
+            "reduction_tflops": flops / 1e12 / (sm[1] / 1e3), "note": "timed region includes regenerating each chunk's weights on the device"}
+
+
+def extra_single_checkpoint_latency(dev, reps: int = 30) -> dict:
+    """What a user of the drop-in sees: `extract_and_analyze_weights(model, device)` on a live ViT-Tiny-shaped module
+    (192d / 6 blocks, timm's module names; run_spectral_analysis.py:297-345), wall clock per call, result dict on the host."""
+    import statistics
+
+    import torch
+    import torch.nn as nn
+
+    from vision_spectra_b200.experiments.run_spectral_analysis import extract_and_analyze_weights
+
+    class Attn(nn.Module):
+        def __init__(self, d):
+            super().__init__()
+            self.qkv, self.proj = nn.Linear(d, 3 * d), nn.Linear(d, d)
+
+    class Mlp(nn.Module):
+        def __init__(self, d):
+            super().__init__()
+            self.fc1, self.fc2 = nn.Linear(d, 4 * d), nn.Linear(4 * d, d)
+
+    class Block(nn.Module):
+        def __init__(self, d):
+            super().__init__()
+            self.attn, self.mlp = Attn(d), Mlp(d)
+
+    class Vit(nn.Module):
+        def __init__(self, d, depth):
+            super().__init__()
+            self.blocks = nn.Sequential(*[Block(d) for _ in range(depth)])
+
+    torch.manual_seed(0)
+    model = Vit(192, 6).to(dev)
+    out = None
+    for _ in range(3):
+        out = extract_and_analyze_weights(model, dev)
+    times = []
+    for _ in range(reps):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        out = extract_and_analyze_weights(model, dev)
+        times.append((time.perf_counter() - t0) * 1e3)
+    return {"workload": "extract_and_analyze_weights on a live ViT-Tiny-shaped module (36 matrices, result dict on the host)",
+            "matrices": len(out["per_layer_metrics"]), "ms_median": statistics.median(times), "ms_min": min(times), "reps": reps}
+
+
+def measure_h2d_ceiling(dev, nbytes: int, sync_all, reps: int = 10) -> float:
+    """Pinned host -> device copy bandwidth (GB/s) of this rank while EVERY rank copies at the same time: the ceiling
+    of the e2e arm's input path on this host (its copies have the same size)."""
+    import torch
+    import torch.distributed as dist
+
+    h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    h.fill_(1)  # touch every page before timing
+    d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        d.copy_(h, non_blocking=True)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        d.copy_(h, non_blocking=True)
+    e1.record()
+    sync_all()
+    gbs = torch.tensor([nbytes * reps / 1e9 / (e0.elapsed_time(e1) / 1e3)], device=dev, dtype=torch.float64)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(gbs, op=dist.ReduceOp.MIN)  # the slowest rank bounds the step
+    return float(gbs.item())
+
+
+def oracle_sample_check(rec, sv, sv_offsets, host_views, n_samples: int = 64, seed: int = 0) -> dict:
+    """Sampled parity check of the LAST timed step against the oracle, outside the timed region: metrics 1e-4,
+    singular values 1e-5 (element-wise), integer outputs exact."""
+    import numpy as np
+
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import spectral_oracle as orc
+
+    rng = np.random.default_rng(seed)
+    idx = rng.choice(len(host_views), size=min(n_samples, len(host_views)), replace=False)
+    worst_m = worst_sv = 0.0
+    for i in idx:
+        w = host_views[i]()
+        ref = orc.get_spectral_metrics(w)
+        for q, k in enumerate(orc.METRIC_KEYS):
+            worst_m = max(worst_m, abs(float(rec["metrics"][i][q]) - ref[k]) / max(abs(ref[k]), 1e-3))
+        io = orc.integer_outputs(w)
+        assert (int(rec["m"][i]), int(rec["start"][i]), int(rec["end"][i]), int(rec["k"][i])) == (io["m"], io["start"], io["end"], io["k"]), i
+        sref = orc.singular_values(w)
+        s = sv[sv_offsets[i] : sv_offsets[i + 1]]
+        worst_sv = max(worst_sv, float(np.max(np.abs(s - sref) / sref)))
+    assert worst_m < 1e-4 and worst_sv < 1e-5, (worst_m, worst_sv)
+    return {"samples": int(len(idx)), "max_metric_rel_err": worst_m, "max_sv_rel_err": worst_sv, "ints_exact": True,
+            "gates": {"metrics": 1e-4, "sv": 1e-5}}
 
 
 # ------------------------------------------------------------------------ GPU arm
@@ -374,6 +641,40 @@ def run_b200_arm(args) -> None:
     d2h_bytes = rec_h.nbytes + (sv_h.nbytes if sv_h is not None else 0)
     assert bool(((rec_h["status"] == 0) | (rec_h["status"] == 96)).all())
     np.testing.assert_allclose(rec_h["metrics"], rec["metrics"], rtol=1e-12)  # same answers both ways
+    # H2D ceiling of this host at this rank count (all ranks copy at once; same copy size as the e2e chunks)
+    e2e_step_s = float(e2e_s.item()) / e2e_steps
+    h2d_achieved = in_bytes / 1e9 / e2e_step_s
+    h2d_ceiling = measure_h2d_ceiling(dev, min(in_bytes, args.chunk * lay.bytes), sync_all)
+
+    # ---------------- sampled parity check of the last e2e step against the oracle (rank 0, outside the timed regions)
+    parity = None
+    if rank == 0:
+        mats_per_ck = lay.matrices
+        sv_off = np.zeros(matrices + 1, np.int64)
+        np.cumsum(np.tile(np.array([min(sl.rows, sl.cols) for sl in lay.slots]), n_ckpt), out=sv_off[1:])
+
+        def view(i):
+            c, m_ = divmod(i, mats_per_ck)
+            sl = lay.slots[m_]
+            return lambda: host_arenas[c][sl.offset : sl.offset + sl.rows * sl.cols].view(sl.rows, sl.cols).numpy()
+
+        parity = oracle_sample_check(rec_h, sv_h, sv_off, [view(i) for i in range(matrices)], n_samples=args.parity_samples)
+
+    # ---------------- the other BASELINE.json configs and the single-checkpoint user path
+    extra = {}
+    if not args.no_extra:
+        del host_block, host_arenas
+        arenas.clear()
+        torch.cuda.empty_cache()
+        six = extra_six_scenario_sweep(eng, dev, world, rank, sync_all)
+        if rank == 0:
+            extra["six_scenario_sweep"] = six
+            extra["scenario_E"] = extra_scenario(eng, dev, "E", lambda: torch.cuda.synchronize(dev))
+            extra["scenario_C"] = extra_scenario(eng, dev, "C", lambda: torch.cuda.synchronize(dev))
+            extra["single_checkpoint_latency"] = extra_single_checkpoint_latency(dev)
+            extra["vit_base_stress"] = extra_vit_base_stress(eng, dev, lambda: torch.cuda.synchronize(dev), ckpts=args.base_ckpts)
+        if world > 1:
+            dist.barrier(device_ids=[local])
 
     if rank != 0:
         if world > 1:
@@ -382,12 +683,15 @@ def run_b200_arm(args) -> None:
 
     # ---------------- roofline of the dominant kernel
     peaks = load_peaks()
-    gram_name = "slice_i8_kernel+gram_i8_mma_kernel"  # stage 1: int8-split Gram on tcgen05 (26 exact int8 MMAs per tile)
-    eig_name = "sbr_band_kernel+band_tridiag_kernel"  # stage 2a: blocked Householder on DMMA.8x8x4 + bulge chasing
+    gram_name = "slice_i8_kernel+gram_i8_mma_kernel"  # stage 1: int8-split Gram on tcgen05 (26 exact digit-pair products)
+    eig_name = "sbr8_kernel+chase8_kernel"  # stage 2a: blocked Householder to bandwidth 8 on DMMA.8x8x4 + bulge chasing
     names = [gram_name, eig_name, "bisect_metrics_kernel"]
     fp64_peak, fp64_src = measure_fp64_peak()
+    i8_n64, i8_n256, i8_src = measure_i8_peak()
     alg = {
-        gram_name: {"bound": "hbm", "work": in_bytes / 1e9, "unit": "GB/s", "peak": peaks["hbm_gbs"],
+        # stage 1 at n = 192 with a 26-pass int8 split is tensor-bound (crossover n = 214 / passes): the
+        # algorithmic 2 n^2 K flops against (measured int8 peak) / 26 digit-pair products per algorithmic one
+        gram_name: {"bound": "tensor", "work": n_ckpt * lay.flops_gram() / 1e12, "unit": "TFLOP/s", "peak": i8_n256 / 26.0,
                     "flops": n_ckpt * lay.flops_gram()},
         # "tensor": the FP64 tensor cores (DMMA.8x8x4); DMMA and DFMA share the same units and the same measured peak
         eig_name: {"bound": "tensor", "work": n_ckpt * lay.flops_tridiag() / 1e12, "unit": "TFLOP/s", "peak": fp64_peak},
@@ -400,9 +704,12 @@ def run_b200_arm(args) -> None:
         st = {"kernel": nm, "ms": float(t), "share": float(t / stage_ms.sum()), "bound": a["bound"],
               "achieved": ach, "peak": a["peak"], "unit": a["unit"],
               "frac": None if ach is None else ach / a["peak"]}
-        if "flops" in a:  # algorithmic 2 n^2 K flops of the Gram stage (the int8 split executes 26x that on the tensor pipe)
-            st["algorithmic_tflops"] = a["flops"] / 1e12 / (t / 1e3)
+        if "flops" in a:  # the int8 split executes 26 digit-pair MMAs (x 2 K-halves of a 64-byte chunk) per algorithmic one
+            st["peak_source"] = i8_src
+            st["int8_peak_tops"] = {"m128n64k32 (production shape)": i8_n64, "m128n256k32": i8_n256}
             st["tensor_int8_tops_executed"] = 26 * a["flops"] / 1e12 / (t / 1e3)
+            st["hbm_gbs"] = in_bytes / 1e9 / (t / 1e3)
+            st["hbm_frac"] = st["hbm_gbs"] / peaks["hbm_gbs"]
         stages.append(st)
     dom = max((s for s in stages if s["achieved"] is not None), key=lambda s: s["ms"])
     roofline = {
@@ -434,7 +741,7 @@ def run_b200_arm(args) -> None:
             )
             cpu = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
         except Exception as exc:  # the GPU numbers stand on their own; say why the baseline is missing
-            cpu = {"value": None, "unit": "matrices/s", "cores": host_cores(), "kind": "port", "sample": f"failed: {exc!r}"}
+            cpu = {"value": None, "unit": "matrices/s", "cores": host_cores(), "kind": reference_kind(), "sample": f"failed: {exc!r}"}
 
     line = {
         "metric": "weight matrices spectrally analysed/sec (ViT-Tiny Q/K/V/MLP)",
@@ -460,12 +767,17 @@ def run_b200_arm(args) -> None:
             "refined_per_gpu_per_step": n_refined,
         },
         "e2e": {"value": e2e_value, "unit": "matrices/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": int(d2h_bytes),
-                "steps": e2e_steps, "api": "vision_spectra_b200.sweep.SweepRunner.run_host (pinned host arenas)"},
+                "steps": e2e_steps, "api": "vision_spectra_b200.sweep.SweepRunner.run_host (pinned host arenas)",
+                "h2d_gbs_achieved_per_gpu": h2d_achieved, "h2d_gbs_ceiling_per_gpu": h2d_ceiling,
+                "h2d_frac": h2d_achieved / h2d_ceiling,
+                "h2d_ceiling_how": "pinned host->device copies of one e2e chunk, every rank copying at the same time, slowest rank"},
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "roofline": roofline,
         "roofline_stages": stages,
         "cpu_baseline": cpu,
+        "parity_check": parity,
+        "extra": extra,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -485,6 +797,9 @@ def main():
                     help="device-resident arm: split the batch over the compute lanes too (measured slower than one launch sequence: 228k vs 243k matrices/s)")
     ap.add_argument("--ref-ckpts", type=int, default=4, help="checkpoints per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the `extra` block (other BASELINE configs, single-checkpoint latency)")
+    ap.add_argument("--parity-samples", type=int, default=64, help="records of the last step checked against the oracle")
+    ap.add_argument("--base-ckpts", type=int, default=16, help="ViT-Base checkpoints of the stress entry of `extra`")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: W >= 3

@@ -68,14 +68,16 @@ def build_native(force: bool = False, verbose: bool = False) -> Path:
 
 
 def build_micro() -> Path:
-    """FP64 tensor-core peak microbenchmark (bench.py runs it on the GPU box for the roofline denominator)."""
-    src = PKG.parent / "scripts" / "micro" / "dmma_bench.cu"
+    """Peak microbenchmarks bench.py runs on the GPU box for the roofline denominators MEASURED_PEAKS.json does not
+    have: FP64 tensor cores (DMMA.8x8x4) and int8 tcgen05.mma."""
     exe = LIB.parent / "dmma_bench"
-    if src.exists():
-        res = subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-o", str(exe), str(src)],
-                             capture_output=True, text=True)
-        if res.returncode != 0:
-            raise RuntimeError("nvcc failed (dmma_bench):\n" + res.stdout + res.stderr)
+    for name in ("dmma_bench", "i8_umma_bench"):
+        src = PKG.parent / "scripts" / "micro" / f"{name}.cu"
+        if src.exists():
+            res = subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-o", str(LIB.parent / name), str(src)],
+                                 capture_output=True, text=True)
+            if res.returncode != 0:
+                raise RuntimeError(f"nvcc failed ({name}):\n" + res.stdout + res.stderr)
     return exe
 
 

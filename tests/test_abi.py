@@ -96,3 +96,17 @@ def test_product_never_imports_oracle():
     bad = re.compile(r"^\s*(?:from|import)\s+(?:scipy|spectral_oracle|oracle)\b|oracle[/\\]|#include\s+\"[^\"]*oracle", re.M)
     for path in list(pkg_dir.rglob("*.py")) + list(pkg_dir.rglob("*.cu")) + list(pkg_dir.rglob("*.cuh")):
         assert not bad.search(path.read_text()), path
+
+
+def test_torch_extension_loads_and_registers_the_op():
+    """lib/vspectra_torch.so (csrc/torch_ext.cpp) loads without a GPU and registers vision_spectra_b200::analyze_batch
+    with the documented schema; calling it with CPU tensors is an error (no fallback kernel is registered)."""
+    import pytest
+    import torch
+    from vision_spectra_b200 import _native as nat
+
+    ops = nat.load_torch_ext()
+    schema = str(torch.ops.vision_spectra_b200.analyze_batch.default._schema)
+    assert "Tensor[] matrices" in schema and "int hill_k=-1" in schema and "bool want_sv=True" in schema
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        ops.analyze_batch([torch.zeros(4, 4)], -1, -1, -1, True)

@@ -75,3 +75,28 @@ def test_gram_views_and_nonfinite():
         ref = _ref_gram(m)
         assert np.max(np.abs(G - ref)) / np.max(np.abs(ref)) < 1e-13
     assert not np.isfinite(got[4][3, 3])  # the poisoned Gram row is flagged on the diagonal
+
+
+def test_gram_within_row_dynamic_range():
+    """The int8 split anchors every Gram row at its largest exponent and keeps 42 bits below it: elements more than 2^17
+    below the row maximum are ROUNDED at 2^-41 of it (gram_i8.cuh).  Outlier columns and single huge entries are the
+    cases where that happens; the Gram matrix must then still be accurate to ~K 2^-42 relative to sqrt(G_ii G_jj)
+    (the eigensolve compensates by re-solving such matrices from W earlier: kRefineRatioInexact), and stay exact
+    (1e-13) when the outliers are within 2^17."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    base = lambda r, c: torch.randn(r, c, generator=g, device="cuda") * 0.02
+    far_cols = base(192, 192)
+    far_cols[:, [3, 77, 150]] *= 1e6  # three outlier columns, 2^20 above the rest
+    far_entry = base(96, 384)
+    far_entry[10, 20] = 3.0e4  # one entry 2^20 above its row
+    far_entry[50, 7] = -1.0e5
+    tall = base(768, 192)
+    tall[:, 5] *= 1e6  # tall: the Gram index is the column -> a whole Gram row is large: exact again
+    near_cols = base(192, 192)
+    near_cols[:, [1, 100]] *= 5e4  # 2^15.6: inside the exact range
+    got = _gram_via_abi([far_cols, far_entry, tall, near_cols])
+    for m, G, tol in zip([far_cols, far_entry, tall, near_cols], got, [1e-10, 1e-10, 1e-13, 1e-12]):
+        ref = _ref_gram(m)
+        dg = np.sqrt(np.maximum(np.diag(ref), 0))
+        err = np.max(np.abs(G - ref) / np.outer(dg, dg))
+        assert np.all(np.isfinite(G)) and err < tol, (tuple(m.shape), err, tol)

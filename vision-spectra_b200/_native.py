@@ -61,6 +61,27 @@ class NativeError(RuntimeError):
     pass
 
 
+TORCH_EXT_PATH = LIB_PATH.parent / "vspectra_torch.so"
+_torch_ops = None
+
+
+def load_torch_ext():
+    """Load lib/vspectra_torch.so (csrc/torch_ext.cpp) and return `torch.ops.vision_spectra_b200`: the PyTorch
+    extension layer over the C-ABI (`analyze_batch`: tensor list in, ATen-owned records / singular values out, on the
+    current stream under a device guard).  Raises if it has not been built; there is no fallback op."""
+    global _torch_ops
+    if _torch_ops is not None:
+        return _torch_ops
+    import torch
+
+    load()  # the C-ABI library first, so that the extension binds to the same copy (VSP_LIB override included)
+    if not TORCH_EXT_PATH.exists():
+        raise NativeError(f"{TORCH_EXT_PATH} is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'`.")
+    torch.ops.load_library(str(TORCH_EXT_PATH))
+    _torch_ops = torch.ops.vision_spectra_b200
+    return _torch_ops
+
+
 _lib = None
 
 

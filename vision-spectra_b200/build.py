@@ -16,6 +16,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "lib" / "libvspectra.so"
+TORCH_EXT = PKG / "lib" / "vspectra_torch.so"
 
 NVCC_FLAGS = [
     "-gencode",
@@ -64,7 +65,30 @@ def build_native(force: bool = False, verbose: bool = False) -> Path:
     if verbose:
         print(res.stderr)
     build_micro()
+    build_torch_ext(force=True)
     return LIB
+
+
+def build_torch_ext(force: bool = False) -> Path:
+    """The PyTorch extension layer (csrc/torch_ext.cpp: torch.ops.vision_spectra_b200.analyze_batch), a host-only C++
+    file over the C-ABI: g++ against the torch headers, linked to lib/libvspectra.so (rpath $ORIGIN), in-tree."""
+    import torch
+    from torch.utils import cpp_extension as ce
+
+    src = CSRC / "torch_ext.cpp"
+    if not force and TORCH_EXT.exists() and TORCH_EXT.stat().st_mtime > max(src.stat().st_mtime, LIB.stat().st_mtime):
+        return TORCH_EXT
+    cuda_home = Path(_nvcc()).resolve().parent.parent
+    tlib = Path(torch.__file__).resolve().parent / "lib"
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
+           "-DTORCH_EXTENSION_NAME=vspectra_torch"]
+    cmd += [f"-I{p}" for p in ce.include_paths()] + [f"-I{cuda_home / 'include'}"]
+    cmd += [str(src), "-o", str(TORCH_EXT), f"-L{tlib}", "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10", "-lc10_cuda",
+            f"-L{LIB.parent}", "-lvspectra", f"-L{cuda_home / 'lib64'}", "-lcudart", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tlib}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed (torch_ext.cpp):\n" + res.stdout + res.stderr[-4000:])
+    return TORCH_EXT
 
 
 def build_micro() -> Path:

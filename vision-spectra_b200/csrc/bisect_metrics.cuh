@@ -375,13 +375,17 @@ constexpr double kRefineRatio = 1e-9;
 // Early test used by the tridiagonalisation kernels (one thread): is there an eigenvalue of
 // T (d, e) below kRefineRatio times the Gershgorin upper bound?  Same product-form recurrence
 // and e^2 floor as sturm_count2.
-VSP_DEV bool has_tiny_eigenvalue(const double* d, const double* e, int n) {
+// Matrices whose int8 digit planes had to round an element (an entry more than 2^17 below the largest one of its Gram
+// row: gram_i8.cuh) carry a Gram error of up to K 2^-42 ||G|| instead of 2^-46: they are re-solved from W already
+// when lambda_min / lambda_max < kRefineRatioInexact, which keeps delta sigma / sigma <= K 2^-43 / ratio ~ 2e-6.
+constexpr double kRefineRatioInexact = 1e-5;
+VSP_DEV bool has_tiny_eigenvalue(const double* d, const double* e, int n, double ratio = kRefineRatio) {
     double gu = 0.0;
     for (int i = 0; i < n; ++i) {
         const double el = (i > 0) ? fabs(e[i - 1]) : 0.0, er = (i < n - 1) ? fabs(e[i]) : 0.0;
         gu = fmax(gu, d[i] + el + er);
     }
-    const double x = kRefineRatio * gu;
+    const double x = ratio * gu;
     double p0 = 1.0, p1 = d[0] - x;
     int changes = (p1 < 0.0) ? 1 : 0;
     for (int i = 1; i < n && changes == 0; ++i) {

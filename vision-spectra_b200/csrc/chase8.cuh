@@ -225,7 +225,8 @@ __global__ void __launch_bounds__(kChase8Threads)
     __syncwarp();
     if (lane == 0) {
         int oflags = 0, slot = -1;
-        if (gate.counter != nullptr && has_tiny_eigenvalue(L, L + n, n)) {  // kappa >~ 3e4: re-solve from W
+        const bool rounded = gate.inexact != nullptr && gate.inexact[item_base + idx] != 0;
+        if (gate.counter != nullptr && has_tiny_eigenvalue(L, L + n, n, rounded ? kRefineRatioInexact : kRefineRatio)) {  // re-solve from W
             slot = atomicAdd(gate.counter, 1);  // list entry (the list holds every item of the class)
             oflags = VSP_ST_ILLCOND;
             gate.slot_items[slot] = item_base + idx;

@@ -107,6 +107,7 @@ struct RefineGate {
     int* counter;     // zeroed by the host before every execution; nullptr = re-solve disabled
     int* slot_items;  // list entry -> position of the flagged item in the plan's item table
     int slots;        // pool buffers = CTAs of the re-solve launch
+    const int* inexact;  // per plan item (sorted position): stage 1 rounded an element of this matrix; may be nullptr
 };
 
 #if !defined(__CUDACC__)

@@ -76,7 +76,8 @@ __global__ void tridiag_global_kernel(const ItemDesc* __restrict__ items, int it
     }
     if (ctx.tid == 0) {
         int oflags = 0, slot = -1;
-        if (gate.counter != nullptr && has_tiny_eigenvalue(d, e, n)) {
+        const bool rounded = gate.inexact != nullptr && gate.inexact[item_base + blockIdx.x] != 0;
+        if (gate.counter != nullptr && has_tiny_eigenvalue(d, e, n, rounded ? kRefineRatioInexact : kRefineRatio)) {
             slot = atomicAdd(gate.counter, 1);  // list entry (the list holds every item of the class)
             oflags = VSP_ST_ILLCOND;
             gate.slot_items[slot] = item_base + blockIdx.x;

@@ -64,17 +64,25 @@ __device__ __forceinline__ int f32_exp_field(unsigned bits) {
 }
 
 // six balanced base-128 digits of x relative to row exponent E, most significant first
-__device__ __forceinline__ void f32_digits(unsigned bits, int E, signed char (&dg)[kDigits]) {
+// Returns the SQUARE of the rounding residual in units of the row's quantum 2^(E-167) (0 for elements within 2^17 of
+// the row maximum, at most 1/4 otherwise).  A Gram row whose residuals add up to more than one quantum (sum of squares
+// > 1: a dozen rounded elements -- outlier columns, a single huge entry; a random-init row has none or one) marks
+// the matrix "rounded": its Gram matrix is then only accurate to ~K 2^-42 ||G|| and the eigensolve hands it to
+// the FP64 re-solve earlier (kRefineRatioInexact, bisect_metrics.cuh).
+__device__ __forceinline__ float f32_digits(unsigned bits, int E, signed char (&dg)[kDigits]) {
     const int exf = (bits >> 23) & 0xff;
     long long man = bits & 0x7fffff;
     if (exf) man |= 0x800000;
     const int sh = 17 - (E - (exf ? exf : 1));
     long long q;
+    float res2 = 0.f;
     if (sh >= 0) {
         q = man << sh;
     } else {
         const int r = -sh;
         q = (r > 40) ? 0 : ((man + (1LL << (r - 1))) >> r);
+        const float res = (r > 40) ? 0.f : (float)(man - (q << r)) * exp2f((float)-r);  // |res| <= 1/2 quantum
+        res2 = res * res;
     }
     if (bits >> 31) q = -q;
 #pragma unroll
@@ -84,13 +92,14 @@ __device__ __forceinline__ void f32_digits(unsigned bits, int E, signed char (&d
         dg[t] = (signed char)dd;
     }
     dg[0] = (signed char)q;
+    return res2;
 }
 
 // One CTA per (item, block of 32 Gram rows).  256 threads.
 //   trans == 0 : Gram row i = row i of W (contiguous K): warp per row.
 //   trans == 1 : Gram row i = column i of W: lanes on columns, digits transposed through smem.
 __global__ void __launch_bounds__(256)
-    slice_i8_kernel(const ItemDesc* __restrict__ items, I8Class cls, unsigned char* __restrict__ wsb) {
+    slice_i8_kernel(const ItemDesc* __restrict__ items, I8Class cls, unsigned char* __restrict__ wsb, int* __restrict__ inexact) {
     const ItemDesc it = items[cls.begin + blockIdx.x];
     const int n = it.n, K = it.kdim, kp = cls.kp;
     const int i0 = blockIdx.y * 32;
@@ -103,6 +112,7 @@ __global__ void __launch_bounds__(256)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ int sE[32];
     __shared__ __align__(16) signed char sdig[kDigits][32][64 + 16];
+    bool any_rounded = false;  // some Gram row of this block accumulated more than one quantum of rounding
 
     if (!it.trans) {
         for (int r = warp; r < 32; r += 8) {
@@ -118,13 +128,14 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) e = max(e, __shfl_xor_sync(0xffffffffu, e, o));
             if (lane == 0) Eout[i] = e;
+            float res2 = 0.f;
             // four consecutive k per lane: one 32-bit store per digit plane
             for (int k = 4 * lane; k < kp; k += 128) {
                 unsigned pk[kDigits] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     signed char dg[kDigits] = {0, 0, 0, 0, 0, 0};
-                    if (k + u < K) f32_digits(__float_as_uint(row[k + u]), e, dg);
+                    if (k + u < K) res2 += f32_digits(__float_as_uint(row[k + u]), e, dg);
 #pragma unroll
                     for (int t = 0; t < kDigits; ++t) pk[t] |= (unsigned)(unsigned char)dg[t] << (8 * u);
                 }
@@ -132,6 +143,9 @@ __global__ void __launch_bounds__(256)
                 for (int t = 0; t < kDigits; ++t)
                     *reinterpret_cast<unsigned*>(planes + ((int64_t)t * n + i) * kp + k) = pk[t];
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) res2 += __shfl_xor_sync(0xffffffffu, res2, o);
+            any_rounded |= res2 > 1.f;
         }
     } else {
         // column maxima: warp w scans rows k = w, w+8, ...; lanes on the 32 columns of this block
@@ -149,11 +163,12 @@ __global__ void __launch_bounds__(256)
         __syncthreads();
         if (tid < 32 && i0 + tid < n) Eout[i0 + tid] = sE[tid];
         const int Ei = sE[lane];
+        float res2 = 0.f;  // this thread's share (rows k = warp mod 8) of Gram row i0 + lane
         for (int k0 = 0; k0 < kp; k0 += 64) {
             for (int kk = warp; kk < 64; kk += 8) {
                 const int k = k0 + kk;
                 signed char dg[kDigits] = {0, 0, 0, 0, 0, 0};
-                if (k < K && i < n) f32_digits(__float_as_uint(W[(int64_t)k * ld + i]), Ei, dg);
+                if (k < K && i < n) res2 += f32_digits(__float_as_uint(W[(int64_t)k * ld + i]), Ei, dg);
 #pragma unroll
                 for (int t = 0; t < kDigits; ++t) sdig[t][lane][kk] = dg[t];
             }
@@ -167,7 +182,18 @@ __global__ void __launch_bounds__(256)
             }
             __syncthreads();
         }
+        // per Gram row: the eight warps' shares meet in shared memory (the digit staging buffer is free now)
+        float* sres = reinterpret_cast<float*>(&sdig[0][0][0]);  // [8][32]
+        sres[warp * 32 + lane] = res2;
+        __syncthreads();
+        if (warp == 0) {
+            float tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) tot += sres[w * 32 + lane];
+            any_rounded |= tot > 1.f;
+        }
     }
+    if (inexact != nullptr && __any_sync(0xffffffffu, any_rounded) && lane == 0) atomicOr(&inexact[cls.begin + blockIdx.x], 1);
 }
 
 // -------------------------------------------------------------------------------- PTX helpers

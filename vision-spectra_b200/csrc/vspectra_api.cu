@@ -111,7 +111,8 @@ struct vsp_plan {
     std::vector<ShapeClass> classes;
     std::vector<I8Class> i8classes;  // fp32 inputs: (n, Kp) groups sharing one digit-plane tensor
     int64_t i8_bytes = 0;            // digit planes + row exponents, after the FP64 region
-    int64_t refine_bytes = 0;        // slot counters (first 1 KB) + FP64 pools, after the int8 region
+    int64_t refine_bytes = 0;        // slot counters (first 1 KB) + rounding flags + FP64 pools, after the int8 region
+    int64_t refine_zero_bytes = 0;   // head of that region that is zeroed before every execution
     int gram_method = 1;             // 1: tcgen05 int8 split (fp32 inputs), 0: FP64 CUDA cores
     int64_t ws_doubles = 0;
     int64_t sv_total = 0;
@@ -162,11 +163,11 @@ int make_plane_map(CUtensorMap* map, void* base, const I8Class& c, int box_rows)
 }
 
 // stage 1 on the tensor cores for every (n, Kp) group of this shape class
-int launch_gram_i8(const vsp_plan* p, const ShapeClass& c, double* ws, unsigned char* wsb, cudaStream_t st) {
+int launch_gram_i8(const vsp_plan* p, const ShapeClass& c, double* ws, unsigned char* wsb, int* inexact, cudaStream_t st) {
     for (const I8Class& g : p->i8classes) {
         if (g.n != c.n) continue;
         dim3 sgrid(g.count, (g.n + 31) / 32);
-        slice_i8_kernel<<<sgrid, 256, 0, st>>>(p->d_items, g, wsb);
+        slice_i8_kernel<<<sgrid, 256, 0, st>>>(p->d_items, g, wsb, inexact);
         g_launches++;
         t_timer.tick("slice_i8", st);
         if (!cuda_ok(cudaGetLastError(), "slice_i8_kernel")) return VSP_E_CUDA;
@@ -363,7 +364,9 @@ static int plan_layout(vsp_plan* p, int32_t count, const int32_t* rows, const in
         if (std::string(e) == "0") p->opts.refine = 0;
     }
     if (p->opts.refine != 0) {
-        int64_t roff = 1024;  // the slot counters live in the first KB
+        int64_t roff = 1024;  // the slot counters live in the first KB,
+        roff += round_up64((int64_t)count * 4, 1024);  // the per-item "stage 1 rounded an element" flags behind them
+        p->refine_zero_bytes = roff;
         int idx = 0;
         for (ShapeClass& c : p->classes) {
             c.refine_slots = 0;
@@ -445,7 +448,8 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
     double* ws = reinterpret_cast<double*>(aligned);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     unsigned char* refine_base = reinterpret_cast<unsigned char*>(ws) + plan_f64_bytes(p) + p->i8_bytes;
-    if (p->refine_bytes > 0) VSP_CUDA(cudaMemsetAsync(refine_base, 0, 1024, st));  // slot counters
+    if (p->refine_bytes > 0) VSP_CUDA(cudaMemsetAsync(refine_base, 0, (size_t)p->refine_zero_bytes, st));  // counters, flags
+    int* inexact = p->refine_bytes > 0 ? reinterpret_cast<int*>(refine_base + 1024) : nullptr;
 
     for (int s = 0; s < p->count; ++s) {
         const void* ptr = d_ptrs[p->order[s]];
@@ -472,16 +476,17 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
         int rc = mark();
         if (rc != VSP_OK) return rc;
         if (p->dtype == VSP_F32 && p->gram_method == 1)
-            rc = launch_gram_i8(p, c, ws, reinterpret_cast<unsigned char*>(ws) + plan_f64_bytes(p), st);
+            rc = launch_gram_i8(p, c, ws, reinterpret_cast<unsigned char*>(ws) + plan_f64_bytes(p), inexact, st);
         else
             rc = (p->dtype == VSP_F32) ? launch_gram<float>(p, c, ws, st) : launch_gram<double>(p, c, ws, st);
         if (rc != VSP_OK) return rc;
         if ((rc = mark()) != VSP_OK) return rc;
-        RefineGate gate{nullptr, nullptr, 0};
+        RefineGate gate{nullptr, nullptr, 0, nullptr};
         if (c.refine_slots > 0) {
             gate.counter = reinterpret_cast<int*>(refine_base) + c.refine_counter;
             gate.slot_items = reinterpret_cast<int*>(refine_base + c.refine_items_off);
             gate.slots = c.refine_slots;
+            gate.inexact = (p->dtype == VSP_F32 && p->gram_method == 1) ? inexact : nullptr;
         }
         if (c.full == kGramTiled) {
             // two-stage reduction, bandwidth 8, matrix resident in shared memory (sbr8.cuh, chase8.cuh).  One launch
@@ -677,7 +682,7 @@ int vsp_plan_debug_gram(vsp_plan* p, const void* const* d_ptrs, double* d_out, v
     for (const ShapeClass& c : p->classes) {
         int rc;
         if (p->dtype == VSP_F32 && p->gram_method == 1)
-            rc = launch_gram_i8(p, c, ws, reinterpret_cast<unsigned char*>(ws) + plan_f64_bytes(p), st);
+            rc = launch_gram_i8(p, c, ws, reinterpret_cast<unsigned char*>(ws) + plan_f64_bytes(p), nullptr, st);
         else
             rc = (p->dtype == VSP_F32) ? launch_gram<float>(p, c, ws, st) : launch_gram<double>(p, c, ws, st);
         if (rc != VSP_OK) return rc;

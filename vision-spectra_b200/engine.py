@@ -14,6 +14,7 @@ CUDA device this module raises.
 from __future__ import annotations
 
 import ctypes
+import os
 from collections import OrderedDict
 from typing import Any, Sequence
 
@@ -91,6 +92,9 @@ class SpectraEngine:
             raise nat.NativeError(f"SpectraEngine needs a CUDA device, got {self.device}")
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
+        # analyze_device goes through the registered torch op when lib/vspectra_torch.so is there (it always is after
+        # build()); VSP_NO_TORCH_OP=1 keeps the ctypes route (same kernels, same results: tests compare the two)
+        self._use_torch_op = nat.TORCH_EXT_PATH.exists() and not os.environ.get("VSP_NO_TORCH_OP")
         self._plans: OrderedDict[tuple, Plan] = OrderedDict()
         self._max_plans = max_cached_plans
         self._ws: torch.Tensor | None = None
@@ -142,6 +146,17 @@ class SpectraEngine:
         dt = tensors[0].dtype
         if dt not in (torch.float32, torch.float64):
             raise TypeError(f"analyze_device takes float32/float64 tensors, got {dt}")
+        if self._use_torch_op:
+            # the PyTorch extension layer: torch.ops.vision_spectra_b200.analyze_batch (csrc/torch_ext.cpp) validates
+            # the tensors, allocates the outputs with ATen and launches on the current stream under a device guard
+            for t in tensors:
+                if t.device != self.device:
+                    raise ValueError("analyze_device: tensors must be on the engine device")
+            fs, fe = (-1, -1) if fit_range is None else (int(fit_range[0]), int(fit_range[1]))
+            records, sv = nat.load_torch_ext().analyze_batch(list(tensors), fs, fe, -1 if hill_k is None else int(hill_k), bool(want_sv))
+            offs = np.zeros(count + 1, np.int64)
+            np.cumsum([min(t.shape) for t in tensors], out=offs[1:])
+            return BatchResult(records.view(-1), sv if want_sv else None, offs, count)
         rows = np.empty(count, np.int32)
         cols = np.empty(count, np.int32)
         ld = np.empty(count, np.int64)

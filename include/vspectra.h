@@ -74,7 +74,12 @@ typedef struct vsp_opts {
     int32_t hill_k;    /* power_law_alpha_hill(k=...)            spectral.py:351     */
     int32_t want_sv;   /* 0: skip the singular-value output; default (-1) = write    */
     int32_t refine;    /* 0: never run the ill-conditioned re-solve; default = auto  */
-    int32_t reserved[3];
+    int32_t dist_k;    /* > 0: also write the first dist_k entries of the four distribution arrays of
+                          get_spectral_distribution (spectral.py:545-557) per matrix -- singular values,
+                          eigenvalues s^2, normalized_sv s/s_0, cumulative_variance cumsum(s^2)/sum(s^2) -- i.e.
+                          SpectralTracker's max_singular_values truncation (spectral.py:683-692) done on the
+                          device: vsp_plan_execute_dist.  0 / -1: off */
+    int32_t reserved[2];
 } vsp_opts;
 
 /* One result record per matrix: 64 bytes, the unit that is gathered across GPUs. */
@@ -132,6 +137,16 @@ void vsp_plan_destroy(vsp_plan* plan);
 int vsp_plan_execute(vsp_plan* plan, const void* const* d_ptrs, double* d_sv,
                      vsp_record* d_records, void* d_workspace, int64_t workspace_bytes,
                      void* stream);
+
+/* vsp_plan_execute for plans created with opts.dist_k > 0: additionally fills
+ *   d_dist      DEVICE f64 [count][4][dist_k]: per matrix (batch order) the rows singular_values, eigenvalues,
+ *               normalized_sv, cumulative_variance, truncated to dist_k entries; entries beyond min(rows, cols)
+ *               and every entry of a matrix with non-finite input are NaN.
+ * d_sv may be NULL when the plan has want_sv == 0: a tracker epoch then moves 4 dist_k values per matrix
+ * instead of min(rows, cols). */
+int vsp_plan_execute_dist(vsp_plan* plan, const void* const* d_ptrs, double* d_sv,
+                          vsp_record* d_records, double* d_dist, void* d_workspace,
+                          int64_t workspace_bytes, void* stream);
 
 /* vsp_plan_execute with CUDA events around each stage.  Synchronises `stream` and
  * returns the device time per stage, summed over shape classes:

@@ -474,8 +474,8 @@ def test_torch_op_matches_ctypes_route_bit_for_bit():
     rec_ref, sv_ref = ref.records_host(), ref.sv_host()
     for stream in (None, torch.cuda.Stream()):
         with torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream()):
-            records, sv = ops.analyze_batch(mats, -1, -1, -1, True)
-            records2, sv2 = torch.ops.vision_spectra_b200.analyze_batch(mats)  # defaults of the schema
+            records, sv, _ = ops.analyze_batch(mats, -1, -1, -1, True, 0)
+            records2, sv2, dist2 = torch.ops.vision_spectra_b200.analyze_batch(mats)  # defaults of the schema
         torch.cuda.synchronize()
         assert records.dtype == torch.uint8 and tuple(records.shape) == (len(mats), 64) and records.is_cuda
         rec = records.cpu().numpy().reshape(-1).view(nat.RECORD_DTYPE)
@@ -493,7 +493,7 @@ def test_torch_op_matches_ctypes_route_bit_for_bit():
     torch.cuda.synchronize()
     np.testing.assert_array_equal(res.records_host()["metrics"], res_c.records_host()["metrics"])
     with pytest.raises(RuntimeError):
-        ops.analyze_batch([torch.zeros(4, 4)], -1, -1, -1, True)  # CPU tensor: no fallback
+        ops.analyze_batch([torch.zeros(4, 4)], -1, -1, -1, True, 0)  # CPU tensor: no fallback
 
 
 def _spectrum_matrix(rng, n, k, sigma, dtype=np.float32):
@@ -533,3 +533,46 @@ def test_accuracy_margins_of_the_gram_route(engine):
         _check_record(name, w, m, s, r, orc.get_spectral_metrics(w), orc.integer_outputs(w), orc.singular_values(w))
         if name.startswith("kappa"):
             assert int(r["status"]) == 0, (name, int(r["status"]))  # Gram route, not re-solved
+
+
+def test_device_distribution_arrays_and_tracker_truncation(engine):
+    """(f)-2 on the device: singular values, eigenvalues, normalized_sv and cumulative_variance of
+    get_spectral_distribution (spectral.py:545-557), truncated to SpectralTracker's max_singular_values
+    (spectral.py:683-692), come out of the metrics kernel (prefix sums included) -- a tracker epoch moves
+    4 k values per matrix instead of min(rows, cols).  Against the oracle's arrays and, through the drop-in
+    get_spectral_distribution / SpectralTracker, against the reference-produced goldens."""
+    from vision_spectra_b200.metrics.spectral import SpectralTracker, get_spectral_distribution
+
+    rng = np.random.default_rng(31)
+    host = [trunc_normal(rng, (192, 192)), trunc_normal(rng, (768, 192)), trunc_normal(rng, (33, 70)), trunc_normal(rng, (5, 9)),
+            np.zeros((12, 12), np.float32), build_case("illcond:50")]
+    k = 50
+    dists: list = []
+    metrics, svs, rec = engine.analyze([torch.from_numpy(np.ascontiguousarray(w)).cuda() for w in host], want_sv=False, dist_k=k, dist_out=dists)
+    assert all(s is None for s in svs)  # want_sv=False: only the truncated arrays travelled
+    for w, d in zip(host, dists):
+        ref = orc.get_spectral_distribution(w)
+        kk = min(k, min(w.shape))
+        assert d.shape == (4, kk)
+        for row, key in enumerate(("singular_values", "eigenvalues", "normalized_sv", "cumulative_variance")):
+            r = np.asarray(ref[key] if isinstance(ref, dict) else getattr(ref, key))[:kk]
+            np.testing.assert_allclose(d[row], r, rtol=2e-5, atol=1e-300, err_msg=f"{w.shape} {key}")
+        assert np.all(np.diff(d[3]) >= -1e-15)  # cumulative variance is monotone
+    nanrow: list = []
+    bad = host[0].copy()
+    bad[3, 4] = np.nan
+    engine.analyze([torch.from_numpy(bad).cuda()], dist_k=8, dist_out=nanrow)
+    assert nanrow[0] is None  # the reference returns no distribution for non-finite input
+    # drop-in level: full-length arrays of one matrix and the tracker's truncated snapshot
+    full = get_spectral_distribution(torch.from_numpy(host[2]).cuda(), name="x", matrix_type="q")
+    ref = orc.get_spectral_distribution(host[2])
+    for key in ("singular_values", "eigenvalues", "normalized_sv", "cumulative_variance"):
+        r = np.asarray(ref[key] if isinstance(ref, dict) else getattr(ref, key))
+        np.testing.assert_allclose(getattr(full, key), r, rtol=2e-5)
+    model = StubViT(embed_dim=96, depth=2, seed=3).cuda()
+    tr = SpectralTracker(max_singular_values=20, include_mlp=True)
+    snap = tr.record_epoch(model, 0)
+    assert len(snap.distributions) == 2 * 6 + 1 and all(len(d.singular_values) == 20 for d in snap.distributions)
+    for d in snap.distributions[:3]:
+        w = dict((n_, p_) for n_, p_ in model.named_parameters())
+        assert d.singular_values[0] >= d.singular_values[-1] > 0 and abs(d.normalized_sv[0] - 1.0) < 1e-15

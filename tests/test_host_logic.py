@@ -206,3 +206,32 @@ def test_state_dict_selection_matches_module_extraction(make, tmp_path):
     ours2 = select_matrices(sd, layer_patterns=["blocks.0"], include_mlp=False, include_patch_embed=True)
     ref2 = orc.extract_all_weights(model, ["blocks.0"], True, True, False, True)
     assert [(w.name, w.matrix_type, tuple(w.shape)) for w in ours2] == [(w.name, w.matrix_type, tuple(w.shape)) for w in ref2]
+
+
+def test_trainer_epoch_artifact_json_layout(tmp_path):
+    """training/base.py:453-511 (JSON half): file name, directory, keys and nesting of spectral_epoch_%04d.json, and
+    the mlflow.log_artifact call with artifact_path 'spectral/json'."""
+    import json
+
+    import numpy as np
+    from vision_spectra_b200.metrics.spectral import EpochSpectralSnapshot, SpectralDistribution
+    from vision_spectra_b200.training.base import save_epoch_spectral_artifacts
+
+    d = SpectralDistribution("blocks.0.attn.qkv.q", "q", np.array([3.0, 2.0, 1.0]), np.array([9.0, 4.0, 1.0]),
+                             np.array([1.0, 2 / 3, 1 / 3]), np.array([9 / 14, 13 / 14, 1.0]),
+                             {"spectral_entropy": 0.9, "stable_rank": 1.5, "alpha_exponent": 1.0, "pl_alpha_hill": 2.0})
+    snap = EpochSpectralSnapshot(epoch=7, distributions=[d], aggregated_metrics={"stable_rank_mean": 1.5})
+    calls = []
+
+    class FakeMlflow:
+        @staticmethod
+        def log_artifact(path, artifact_path=None):
+            calls.append((path, artifact_path))
+
+    out = save_epoch_spectral_artifacts(snap, 7, tmp_path, FakeMlflow)
+    assert out == tmp_path / "spectral" / "json" / "spectral_epoch_0007.json"
+    data = json.loads(out.read_text())
+    assert list(data) == ["epoch", "timestamp", "aggregated_metrics", "distributions"] and data["epoch"] == 7
+    assert list(data["distributions"][0]) == ["name", "matrix_type", "singular_values", "metrics"]
+    assert data["distributions"][0]["singular_values"] == [3.0, 2.0, 1.0]
+    assert calls == [(str(out), "spectral/json")]

@@ -44,16 +44,18 @@ class VspOpts(ctypes.Structure):
         ("hill_k", c_int32),
         ("want_sv", c_int32),
         ("refine", c_int32),
-        ("reserved", c_int32 * 3),
+        ("dist_k", c_int32),
+        ("reserved", c_int32 * 2),
     ]
 
     @classmethod
-    def make(cls, fit_range=None, hill_k=None, want_sv=True, refine=None):
+    def make(cls, fit_range=None, hill_k=None, want_sv=True, refine=None, dist_k=0):
         o = cls()
         o.fit_start, o.fit_end = (-1, -1) if fit_range is None else (int(fit_range[0]), int(fit_range[1]))
         o.hill_k = -1 if hill_k is None else int(hill_k)
         o.want_sv = 1 if want_sv else 0
         o.refine = -1 if refine is None else int(bool(refine))
+        o.dist_k = max(0, int(dist_k or 0))
         return o
 
 
@@ -108,6 +110,7 @@ def load() -> ctypes.CDLL:
         "vsp_plan_sv_count": (c_int64, [c_void_p]),
         "vsp_plan_destroy": (None, [c_void_p]),
         "vsp_plan_execute": (c_int32, [c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+        "vsp_plan_execute_dist": (c_int32, [c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
         "vsp_plan_execute_profiled": (
             c_int32,
             [c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, POINTER(ctypes.c_float)],
@@ -143,6 +146,7 @@ EXPORTED_SYMBOLS = (
     "vsp_plan_sv_count",
     "vsp_plan_destroy",
     "vsp_plan_execute",
+    "vsp_plan_execute_dist",
     "vsp_plan_execute_profiled",
     "vsp_plan_debug_gram",
     "vsp_analyze_batch",

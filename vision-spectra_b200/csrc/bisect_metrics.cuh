@@ -411,11 +411,16 @@ struct MetricOut {
 // lam[] ascending, in scaled units (scale = power of four applied to the Gram
 // matrix).  Writes sv[0..n) descending (if sv != nullptr) and returns the record
 // fields.  `flags` carries VSP_ST_NONFINITE / VSP_ST_ZERO from the Gram stage.
+// dist != nullptr: also the first dist_k entries of the distribution arrays of get_spectral_distribution
+// (spectral.py:545-557), rows sv | sv^2 | sv / sv_0 | cumsum(sv^2) / sum(sv^2) of a [4][dist_k] block; NaN beyond n.
 template <class Ctx>
 VSP_DEV MetricOut spectral_metrics(Ctx& ctx, double* lam, int n, double scale, int flags,
-                                   int fit_start, int fit_end, int hill_k, double* sv) {
+                                   int fit_start, int fit_end, int hill_k, double* sv, double* dist = nullptr, int dist_k = 0) {
     MetricOut out;
     const double nan = NAN;
+    if (dist_k <= 0) dist = nullptr;
+    if (dist)  // NaN everywhere first: the failure paths below and the entries beyond n keep it
+        for (int i = ctx.tid; i < 4 * dist_k; i += ctx.nthreads) dist[i] = nan;
     out.metrics[0] = out.metrics[1] = out.metrics[2] = out.metrics[3] = nan;
     out.m = 0;
     out.start = out.end = out.k = -1;
@@ -430,6 +435,11 @@ VSP_DEV MetricOut spectral_metrics(Ctx& ctx, double* lam, int n, double scale, i
         out.status |= VSP_ST_ZERO;
         if (sv)
             for (int i = ctx.tid; i < n; i += ctx.nthreads) sv[i] = 0.0;
+        if (dist) {  // all-zero matrix: s = 0, s_max -> 1, total variance 0 -> zeros (spectral.py:548-555)
+            ctx.sync();
+            for (int i = ctx.tid; i < 4 * dist_k; i += ctx.nthreads)
+                if (i % dist_k < n) dist[i] = 0.0;
+        }
         return out;
     }
     // Eigenvalues of a Gram matrix are >= 0; rounding can push the smallest ones to
@@ -461,6 +471,21 @@ VSP_DEV MetricOut spectral_metrics(Ctx& ctx, double* lam, int n, double scale, i
     }
     out.metrics[0] = ctx.sum(h);
     out.metrics[1] = total / lmax;
+    if (dist) {
+        // entry i: sequential partial sum of the i + 1 largest eigenvalues, as np.cumsum forms it (dist_k is small:
+        // SpectralTracker's max_singular_values; the full-length case costs n additions per thread once)
+        const double unscale = sqrt(1.0 / scale), s0 = sqrt(lmax) * unscale;
+        const int kk = dist_k < n ? dist_k : n;
+        for (int i = ctx.tid; i < kk; i += ctx.nthreads) {
+            double c = 0.0;
+            for (int j = 0; j <= i; ++j) c += lam[n - 1 - j];
+            const double s = sqrt(lam[n - 1 - i]) * unscale;
+            dist[i] = s;
+            dist[dist_k + i] = s * s;
+            dist[2 * dist_k + i] = s / s0;
+            dist[3 * dist_k + i] = c / total;
+        }
+    }
 
     // ---- alpha: OLS slope of ln sigma on ln rank over [start, end)
     int start = -1, end = -1;

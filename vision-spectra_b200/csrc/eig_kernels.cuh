@@ -93,7 +93,7 @@ __global__ void tridiag_global_kernel(const ItemDesc* __restrict__ items, int it
 template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) bisect_metrics_kernel(const ItemDesc* __restrict__ items, int item_base,
                                       const double* __restrict__ ws, int npad, vsp_opts opts,
-                                      double* __restrict__ sv_out, vsp_record* __restrict__ records) {
+                                      double* __restrict__ sv_out, vsp_record* __restrict__ records, double* __restrict__ dist_out) {
     extern __shared__ __align__(16) double smem[];
     const ItemDesc it = items[item_base + blockIdx.x];
     const int n = it.n;
@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(MAXT, MINB) bisect_metrics_kernel(const ItemDe
     }
     iters = ctx.max_i(iters);  // barrier: lam[] complete
     double* sv = (opts.want_sv != 0 && sv_out != nullptr) ? sv_out + it.sv_off : nullptr;
-    const MetricOut mo = spectral_metrics(ctx, lam, n, scale, flags, opts.fit_start, opts.fit_end, opts.hill_k, sv);
+    double* dist = (dist_out != nullptr && opts.dist_k > 0) ? dist_out + (int64_t)it.item * 4 * opts.dist_k : nullptr;
+    const MetricOut mo = spectral_metrics(ctx, lam, n, scale, flags, opts.fit_start, opts.fit_end, opts.hill_k, sv, dist, opts.dist_k);
     if (ctx.tid == 0) {
         vsp_record r;
         r.item = it.item;
@@ -165,7 +166,7 @@ __host__ __device__ inline size_t refine_smem_fixed_bytes(int npad) {
 template <typename TIn>
 __global__ void __launch_bounds__(1024)
     refine_kernel(const ItemDesc* __restrict__ items, RefineGate gate, RefinePool pool, int npad, int xs_doubles,
-                  vsp_opts opts, double* __restrict__ sv_out, vsp_record* __restrict__ records) {
+                  vsp_opts opts, double* __restrict__ sv_out, vsp_record* __restrict__ records, double* __restrict__ dist_out) {
     extern __shared__ __align__(16) double smem[];
     const int slot = blockIdx.x;
     const int nflagged = *gate.counter;
@@ -226,7 +227,8 @@ __global__ void __launch_bounds__(1024)
     int iters = gk_singular_values(ctx, dq, eq, n, de, lam);
     iters = ctx.max_i(iters);  // barrier: lam[] complete
     double* sv = (opts.want_sv != 0 && sv_out != nullptr) ? sv_out + it.sv_off : nullptr;
-    const MetricOut mo = spectral_metrics(ctx, lam, n, sc * sc, 0, opts.fit_start, opts.fit_end, opts.hill_k, sv);
+    double* dist = (dist_out != nullptr && opts.dist_k > 0) ? dist_out + (int64_t)it.item * 4 * opts.dist_k : nullptr;
+    const MetricOut mo = spectral_metrics(ctx, lam, n, sc * sc, 0, opts.fit_start, opts.fit_end, opts.hill_k, sv, dist, opts.dist_k);
     if (ctx.tid == 0) {
         vsp_record r;
         r.item = it.item;

@@ -85,13 +85,13 @@ __device__ __forceinline__ float f32_digits(unsigned bits, int E, signed char (&
         res2 = res * res;
     }
     if (bits >> 31) q = -q;
+    // balanced digits s_t in [-64, 63] (s_0 up to 64) of q = ordinary base-128 digits of q + 64 (128^5 + ... + 1), minus 64:
+    // no carry chain, six shift-and-mask steps
+    constexpr long long kBias = 64LL * ((1LL << 42) - 1) / 127;
+    const unsigned long long qb = (unsigned long long)(q + kBias);  // 0 <= qb < 129 * 128^5
+    dg[0] = (signed char)((int)(qb >> 35) - 64);
 #pragma unroll
-    for (int t = kDigits - 1; t >= 1; --t) {
-        const long long dd = ((q + 64) & 127) - 64;
-        q = (q - dd) >> 7;
-        dg[t] = (signed char)dd;
-    }
-    dg[0] = (signed char)q;
+    for (int t = 1; t < kDigits; ++t) dg[t] = (signed char)((int)((qb >> (7 * (kDigits - 1 - t))) & 127) - 64);
     return res2;
 }
 
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256)
     int* __restrict__ Eout = reinterpret_cast<int*>(wsb + cls.exp_off) + (int64_t)blockIdx.x * n;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ int sE[32];
-    __shared__ __align__(16) signed char sdig[kDigits][32][64 + 16];
+    __shared__ __align__(16) signed char sdig[kDigits][32][17 * 4];  // [plane][Gram row][17 words]: see the transposing branch
     bool any_rounded = false;  // some Gram row of this block accumulated more than one quantum of rounding
 
     if (!it.trans) {
@@ -129,13 +129,23 @@ __global__ void __launch_bounds__(256)
             for (int o = 16; o > 0; o >>= 1) e = max(e, __shfl_xor_sync(0xffffffffu, e, o));
             if (lane == 0) Eout[i] = e;
             float res2 = 0.f;
-            // four consecutive k per lane: one 32-bit store per digit plane
+            // four consecutive k per lane: one 128-bit load (when the row is 16-byte aligned), one 32-bit store per plane
+            const bool vec = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
             for (int k = 4 * lane; k < kp; k += 128) {
                 unsigned pk[kDigits] = {0, 0, 0, 0, 0, 0};
+                float xv[4] = {0.f, 0.f, 0.f, 0.f};
+                if (vec && k + 3 < K) {
+                    const float4 f = *reinterpret_cast<const float4*>(row + k);
+                    xv[0] = f.x, xv[1] = f.y, xv[2] = f.z, xv[3] = f.w;
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (k + u < K) xv[u] = row[k + u];
+                }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     signed char dg[kDigits] = {0, 0, 0, 0, 0, 0};
-                    if (k + u < K) res2 += f32_digits(__float_as_uint(row[k + u]), e, dg);
+                    if (k + u < K) res2 += f32_digits(__float_as_uint(xv[u]), e, dg);
 #pragma unroll
                     for (int t = 0; t < kDigits; ++t) pk[t] |= (unsigned)(unsigned char)dg[t] << (8 * u);
                 }
@@ -163,22 +173,36 @@ __global__ void __launch_bounds__(256)
         __syncthreads();
         if (tid < 32 && i0 + tid < n) Eout[i0 + tid] = sE[tid];
         const int Ei = sE[lane];
-        float res2 = 0.f;  // this thread's share (rows k = warp mod 8) of Gram row i0 + lane
+        float res2 = 0.f;  // this thread's share of Gram row i0 + lane
+        // digits staged as 32-bit words (four consecutive k of one Gram row), row pitch 17 words: lanes (= Gram rows) fall
+        // into different banks (the byte-granular staging at an 80-byte pitch ran at 4-way conflicts: ncu r01)
+        unsigned(*sw)[32][17] = reinterpret_cast<unsigned(*)[32][17]>(&sdig[0][0][0]);
         for (int k0 = 0; k0 < kp; k0 += 64) {
-            for (int kk = warp; kk < 64; kk += 8) {
-                const int k = k0 + kk;
-                signed char dg[kDigits] = {0, 0, 0, 0, 0, 0};
-                if (k < K && i < n) res2 += f32_digits(__float_as_uint(W[(int64_t)k * ld + i]), Ei, dg);
 #pragma unroll
-                for (int t = 0; t < kDigits; ++t) sdig[t][lane][kk] = dg[t];
+            for (int j = 0; j < 2; ++j) {
+                const int kw = warp + 8 * j;  // word index inside the 64-byte chunk: k = k0 + 4 kw .. + 3
+                unsigned pk[kDigits] = {0, 0, 0, 0, 0, 0};
+                float xv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = k0 + 4 * kw + u;
+                    xv[u] = (k < K && i < n) ? W[(int64_t)k * ld + i] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    signed char dg[kDigits] = {0, 0, 0, 0, 0, 0};
+                    if (k0 + 4 * kw + u < K && i < n) res2 += f32_digits(__float_as_uint(xv[u]), Ei, dg);
+#pragma unroll
+                    for (int t = 0; t < kDigits; ++t) pk[t] |= (unsigned)(unsigned char)dg[t] << (8 * u);
+                }
+#pragma unroll
+                for (int t = 0; t < kDigits; ++t) sw[t][lane][kw] = pk[t];
             }
             __syncthreads();
-            // 6 planes x 32 rows x 64 bytes = 768 16-byte vectors, coalesced 64-byte runs
-            for (int v = tid; v < kDigits * 32 * 4; v += 256) {
-                const int t = v / 128, r = (v >> 2) & 31, c = v & 3;
-                if (i0 + r < n)
-                    *reinterpret_cast<uint4*>(planes + ((int64_t)t * n + i0 + r) * kp + k0 + 16 * c) =
-                        *reinterpret_cast<const uint4*>(&sdig[t][r][16 * c]);
+            // 6 planes x 32 rows x 16 words: 64-byte runs per Gram row
+            for (int v = tid; v < kDigits * 32 * 16; v += 256) {
+                const int t = v >> 9, r = (v >> 4) & 31, c = v & 15;
+                if (i0 + r < n) *reinterpret_cast<unsigned*>(planes + ((int64_t)t * n + i0 + r) * kp + k0 + 4 * c) = sw[t][r][c];
             }
             __syncthreads();
         }

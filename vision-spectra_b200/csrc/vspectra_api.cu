@@ -279,6 +279,7 @@ static int plan_layout(vsp_plan* p, int32_t count, const int32_t* rows, const in
         p->opts.fit_start = p->opts.fit_end = p->opts.hill_k = -1;
         p->opts.want_sv = -1;
         p->opts.refine = -1;
+        p->opts.dist_k = 0;
     }
     // caller-order SV offsets
     std::vector<int64_t> sv_off(count + 1, 0);
@@ -435,11 +436,13 @@ void vsp_plan_destroy(vsp_plan* plan) {
 }
 
 static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vsp_record* d_records,
-                        void* d_workspace, int64_t workspace_bytes, void* stream, std::vector<cudaEvent_t>* evs) {
+                        void* d_workspace, int64_t workspace_bytes, void* stream, std::vector<cudaEvent_t>* evs,
+                        double* d_dist = nullptr) {
     if (!p) return VSP_E_ARG;
     if (p->count == 0) return VSP_OK;
     if (!d_ptrs || !d_records || !d_workspace) return VSP_E_ARG;
     if (p->opts.want_sv != 0 && !d_sv) return VSP_E_ARG;
+    if (p->opts.dist_k > 0 && !d_dist) return VSP_E_ARG;  // a distribution plan needs vsp_plan_execute_dist
     // align the workspace to 256 bytes inside the caller's buffer
     uintptr_t base = reinterpret_cast<uintptr_t>(d_workspace);
     uintptr_t aligned = (base + 255) & ~uintptr_t(255);
@@ -615,10 +618,10 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
             VSP_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
             if (p->dtype == VSP_F32) {
                 VSP_CUDA(cudaFuncSetAttribute(refine_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                refine_kernel<float><<<c.refine_slots, 1024, rsm, st>>>(p->d_items, gate, pool, c.npad, xs_doubles, p->opts, d_sv, d_records);
+                refine_kernel<float><<<c.refine_slots, 1024, rsm, st>>>(p->d_items, gate, pool, c.npad, xs_doubles, p->opts, d_sv, d_records, d_dist);
             } else {
                 VSP_CUDA(cudaFuncSetAttribute(refine_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                refine_kernel<double><<<c.refine_slots, 1024, rsm, st>>>(p->d_items, gate, pool, c.npad, xs_doubles, p->opts, d_sv, d_records);
+                refine_kernel<double><<<c.refine_slots, 1024, rsm, st>>>(p->d_items, gate, pool, c.npad, xs_doubles, p->opts, d_sv, d_records, d_dist);
             }
             g_launches++;
             t_timer.tick("refine", st);
@@ -628,10 +631,10 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
         const int bthreads = bisect_threads(c.n);
         if (bthreads <= 128)
             bisect_metrics_kernel<128, 6><<<c.count, bthreads, bisect_smem_bytes(c.npad), bst>>>(p->d_items, c.begin, ws, c.npad,
-                                                                                                 p->opts, d_sv, d_records);
+                                                                                                 p->opts, d_sv, d_records, d_dist);
         else
             bisect_metrics_kernel<1024, 1><<<c.count, bthreads, bisect_smem_bytes(c.npad), bst>>>(p->d_items, c.begin, ws, c.npad,
-                                                                                                  p->opts, d_sv, d_records);
+                                                                                                  p->opts, d_sv, d_records, d_dist);
         g_launches++;
         t_timer.tick("bisect", bst);
         VSP_CUDA(cudaGetLastError());
@@ -706,6 +709,12 @@ int vsp_plan_debug_gram(vsp_plan* p, const void* const* d_ptrs, double* d_out, v
 int vsp_plan_execute(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vsp_record* d_records,
                      void* d_workspace, int64_t workspace_bytes, void* stream) {
     return execute_impl(p, d_ptrs, d_sv, d_records, d_workspace, workspace_bytes, stream, nullptr);
+}
+
+int vsp_plan_execute_dist(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vsp_record* d_records, double* d_dist,
+                          void* d_workspace, int64_t workspace_bytes, void* stream) {
+    if (!p || p->opts.dist_k <= 0 || !d_dist) return VSP_E_ARG;
+    return execute_impl(p, d_ptrs, d_sv, d_records, d_workspace, workspace_bytes, stream, nullptr, d_dist);
 }
 
 int vsp_plan_execute_profiled(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vsp_record* d_records,

@@ -35,13 +35,18 @@ def nan_metrics() -> dict[str, float]:
 class BatchResult:
     """Records + singular values of one executed batch, still on the device."""
 
-    __slots__ = ("records", "sv", "sv_offsets", "count")
+    __slots__ = ("records", "sv", "sv_offsets", "count", "dist")
 
-    def __init__(self, records: torch.Tensor, sv: torch.Tensor | None, sv_offsets: np.ndarray, count: int):
+    def __init__(self, records: torch.Tensor, sv: torch.Tensor | None, sv_offsets: np.ndarray, count: int,
+                 dist: torch.Tensor | None = None):
         self.records = records  # uint8 [count*64]
         self.sv = sv  # float64 [sum n] or None
         self.sv_offsets = sv_offsets  # int64 [count+1]
         self.count = count
+        self.dist = dist  # float64 [count, 4, dist_k] or None: sv | sv^2 | sv/sv_0 | cumulative variance, truncated
+
+    def dist_host(self) -> np.ndarray | None:
+        return None if self.dist is None else self.dist.cpu().numpy()
 
     def records_host(self) -> np.ndarray:
         return self.records.cpu().numpy().view(nat.RECORD_DTYPE)
@@ -103,7 +108,7 @@ class SpectraEngine:
 
     # ------------------------------------------------------------------ plans
     def _plan(self, rows, cols, ld, dtype: int, opts: nat.VspOpts) -> Plan:
-        key = (rows.tobytes(), cols.tobytes(), ld.tobytes(), dtype, opts.fit_start, opts.fit_end, opts.hill_k, opts.want_sv, opts.refine)
+        key = (rows.tobytes(), cols.tobytes(), ld.tobytes(), dtype, opts.fit_start, opts.fit_end, opts.hill_k, opts.want_sv, opts.refine, opts.dist_k)
         plan = self._plans.get(key)
         if plan is not None:
             self._plans.move_to_end(key)
@@ -136,6 +141,7 @@ class SpectraEngine:
         fit_range: tuple[int, int] | None = None,
         hill_k: int | None = None,
         want_sv: bool = True,
+        dist_k: int = 0,
     ) -> BatchResult:
         """Launch the three stages for 2-D CUDA tensors of ONE dtype (float32 or
         float64) with unit column stride.  Asynchronous on the current stream;
@@ -153,10 +159,11 @@ class SpectraEngine:
                 if t.device != self.device:
                     raise ValueError("analyze_device: tensors must be on the engine device")
             fs, fe = (-1, -1) if fit_range is None else (int(fit_range[0]), int(fit_range[1]))
-            records, sv = nat.load_torch_ext().analyze_batch(list(tensors), fs, fe, -1 if hill_k is None else int(hill_k), bool(want_sv))
+            records, sv, dist = nat.load_torch_ext().analyze_batch(list(tensors), fs, fe, -1 if hill_k is None else int(hill_k),
+                                                                   bool(want_sv), int(dist_k or 0))
             offs = np.zeros(count + 1, np.int64)
             np.cumsum([min(t.shape) for t in tensors], out=offs[1:])
-            return BatchResult(records.view(-1), sv if want_sv else None, offs, count)
+            return BatchResult(records.view(-1), sv if want_sv else None, offs, count, dist if dist_k else None)
         rows = np.empty(count, np.int32)
         cols = np.empty(count, np.int32)
         ld = np.empty(count, np.int64)
@@ -170,7 +177,7 @@ class SpectraEngine:
                 raise ValueError("analyze_device: overlapping rows (stride(0) < cols)")
             ptrs[i] = t.data_ptr()
         dtype = nat.VSP_F32 if dt == torch.float32 else nat.VSP_F64
-        return self.analyze_raw(ptrs, rows, cols, ld, dtype, fit_range, hill_k, want_sv)
+        return self.analyze_raw(ptrs, rows, cols, ld, dtype, fit_range, hill_k, want_sv, dist_k=dist_k)
 
     def analyze_raw(
         self,
@@ -186,6 +193,7 @@ class SpectraEngine:
         stage_ms: list | None = None,
         out_records: torch.Tensor | None = None,
         out_sv: torch.Tensor | None = None,
+        dist_k: int = 0,
     ) -> BatchResult:
         """Table form of analyze_device: `ptrs` is a uint64 array of device addresses,
         rows/cols int32, ld int64 (elements).  The caller keeps the memory alive until
@@ -194,7 +202,7 @@ class SpectraEngine:
         count = int(len(ptrs))
         ptrs = np.ascontiguousarray(ptrs, dtype=np.uint64)
         if plan is None:
-            plan = self.make_plan(rows, cols, ld, dtype, fit_range, hill_k, want_sv)
+            plan = self.make_plan(rows, cols, ld, dtype, fit_range, hill_k, want_sv, dist_k)
         if plan.handle is None:
             raise nat.NativeError("analyze_raw: the plan has been closed")
         ws_bytes = self.lib.vsp_plan_workspace_bytes(plan.handle)
@@ -217,6 +225,14 @@ class SpectraEngine:
             int(self._ws.numel()),
             stream,
         )
+        dist = None
+        if dist_k:
+            dist = torch.empty((count, 4, int(dist_k)), dtype=torch.float64, device=self.device)
+            with torch.cuda.device(self.device):
+                nat.check(self.lib.vsp_plan_execute_dist(*args[:4], dist.data_ptr(), *args[4:]), "vsp_plan_execute_dist")
+            offs = np.zeros(count + 1, np.int64)
+            np.cumsum(np.minimum(rows, cols), out=offs[1:])
+            return BatchResult(records, sv, offs, count, dist)
         with torch.cuda.device(self.device):
             if stage_ms is None:
                 nat.check(self.lib.vsp_plan_execute(*args), "vsp_plan_execute")
@@ -228,10 +244,10 @@ class SpectraEngine:
         np.cumsum(np.minimum(rows, cols), out=offs[1:])
         return BatchResult(records, sv, offs, count)
 
-    def make_plan(self, rows, cols, ld, dtype: int, fit_range=None, hill_k=None, want_sv: bool = True) -> Plan:
+    def make_plan(self, rows, cols, ld, dtype: int, fit_range=None, hill_k=None, want_sv: bool = True, dist_k: int = 0) -> Plan:
         """Validated, device-resident shape table for a batch (cached per engine; the returned `Plan` stays
         valid for as long as the caller holds it, whatever the cache evicts)."""
-        opts = nat.VspOpts.make(fit_range, hill_k, want_sv)
+        opts = nat.VspOpts.make(fit_range, hill_k, want_sv, dist_k=dist_k)
         return self._plan(nat.i32(rows), nat.i32(cols), nat.i64(ld), dtype, opts)
 
     # ----------------------------------------------------------------- host path
@@ -266,12 +282,18 @@ class SpectraEngine:
         fit_range: tuple[int, int] | None = None,
         hill_k: int | None = None,
         want_sv: bool = True,
+        dist_k: int = 0,
+        dist_out: list | None = None,
     ) -> tuple[list[dict[str, float]], list[np.ndarray | None], np.ndarray]:
         """Analyse a ragged list of matrices (torch tensors on any device or NumPy
         arrays, any float dtype).  Returns (metrics dicts, singular-value arrays,
         records) in input order.  Anything the reference would answer with NaN
         (non-2-D input, empty matrix, NaN/Inf entries) yields NaN metrics and
         `None` singular values; nothing raises for bad *data*.
+
+        `dist_k > 0` asks for the device-computed distribution arrays (spectral.py:545-557) truncated to `dist_k`
+        entries (SpectralTracker's max_singular_values); they are appended to the list `dist_out`, one [4, min(n, dist_k)]
+        array per matrix (None where the reference returns no distribution).
 
         float32 / float16 / bfloat16 inputs are analysed from their (exactly widened) float32 values; float64,
         integer and extended-precision inputs from float64, as the reference's `np.asarray(w, dtype=np.float64)`
@@ -321,18 +343,24 @@ class SpectraEngine:
         for tdt, lst in groups.items():
             if lst:
                 lst.sort(key=lambda p: p[0])
-                res = self.analyze_device([t for _, t in lst], fit_range, hill_k, want_sv)
+                res = self.analyze_device([t for _, t in lst], fit_range, hill_k, want_sv, dist_k)
                 pending.append((lst, res))
+        dists: list = [None] * count
         for lst, res in pending:
             rec = res.records_host()
             sv = res.sv_host()
-            for j, (i, _) in enumerate(lst):
+            dh = res.dist_host()
+            for j, (i, t) in enumerate(lst):
+                if dh is not None and not (int(rec[j]["status"]) & nat.ST_NONFINITE):
+                    dists[i] = dh[j][:, : min(int(dist_k), min(t.shape))].copy()
                 r = rec[j]
                 records[i] = r
                 records[i]["item"] = i
                 metrics[i] = {k: float(r["metrics"][q]) for q, k in enumerate(METRIC_KEYS)}
                 if sv is not None and not (int(r["status"]) & nat.ST_NONFINITE):
                     svs[i] = sv[res.sv_offsets[j] : res.sv_offsets[j + 1]].copy()
+        if dist_out is not None:
+            dist_out[:] = dists
         return metrics, svs, records
 
 

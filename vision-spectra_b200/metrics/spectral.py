@@ -141,13 +141,26 @@ def distribution_from_sv(
     )
 
 
+def distribution_from_device(d: np.ndarray | None, metrics: dict[str, float], name: str = "", matrix_type: str = "unknown") -> SpectralDistribution | None:
+    """SpectralDistribution from the [4, k] block the metrics kernel wrote (rows: singular values, eigenvalues,
+    normalized_sv, cumulative_variance -- spectral.py:545-557 computed on the device, truncated to k entries)."""
+    if d is None:
+        return None
+    return SpectralDistribution(name=name, matrix_type=matrix_type, singular_values=d[0], eigenvalues=d[1],
+                                normalized_sv=d[2], cumulative_variance=d[3], metrics=metrics)
+
+
 def get_spectral_distribution(weight_matrix, name: str = "", matrix_type: str = "unknown") -> SpectralDistribution | None:
     """Full distribution of one matrix; None for non-2-D input or failed SVD.
-    Reference spectral.py:495-570."""
+    Reference spectral.py:495-570.  The four arrays come from the device (full length: dist_k = min(rows, cols))."""
     if not _is_2d(weight_matrix):
         return None
-    metrics, svs = analyze_matrices([weight_matrix])
-    return distribution_from_sv(svs[0], metrics[0], name, matrix_type)
+    from ..engine import default_engine
+
+    dev = weight_matrix.device if hasattr(weight_matrix, "device") and getattr(weight_matrix.device, "type", "") == "cuda" else None
+    dists: list = []
+    metrics, _, _ = default_engine(dev).analyze([weight_matrix], want_sv=False, dist_k=max(1, min(weight_matrix.shape)), dist_out=dists)
+    return distribution_from_device(dists[0], metrics[0], name, matrix_type)
 
 
 @dataclass
@@ -197,24 +210,20 @@ class SpectralTracker:
             include_mlp=self.include_mlp,
             include_patch_embed=self.include_patch_embed,
         )
-        metrics, svs = analyze_matrices([w.weight for w in weights]) if weights else ([], [])
+        # one batched call; the truncation to max_singular_values (reference :683-692) happens in the metrics kernel,
+        # so 4 k values per matrix come back instead of min(rows, cols) singular values
+        from ..engine import default_engine
+
         distributions = []
-        k = self.max_singular_values
-        for w, m, s in zip(weights, metrics, svs):
-            dist = distribution_from_sv(s, m, w.name, w.matrix_type)
-            if dist is None:
-                continue
-            if len(dist.singular_values) > k:
-                dist = SpectralDistribution(
-                    name=dist.name,
-                    matrix_type=dist.matrix_type,
-                    singular_values=dist.singular_values[:k],
-                    eigenvalues=dist.eigenvalues[:k],
-                    normalized_sv=dist.normalized_sv[:k],
-                    cumulative_variance=dist.cumulative_variance[:k],
-                    metrics=dist.metrics,
-                )
-            distributions.append(dist)
+        if weights:
+            dev = next((w.weight.device for w in weights if getattr(w.weight, "is_cuda", False)), None)
+            dists: list = []
+            metrics, _, _ = default_engine(dev).analyze([w.weight for w in weights], want_sv=False,
+                                                        dist_k=max(1, int(self.max_singular_values)), dist_out=dists)
+            for w, m, d in zip(weights, metrics, dists):
+                dist = distribution_from_device(d, m, w.name, w.matrix_type)
+                if dist is not None:
+                    distributions.append(dist)
         all_metrics = [d.metrics for d in distributions]
         snapshot = EpochSpectralSnapshot(
             epoch=epoch,

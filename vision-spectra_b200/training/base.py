@@ -4,6 +4,7 @@ from __future__ import annotations
 
 from typing import Any
 
+import numpy as np
 import torch
 
 from ..engine import analyze_matrices
@@ -42,3 +43,31 @@ class SpectralTrainerMixin:
 
     def _compute_spectral_metrics(self) -> dict[str, float]:
         return compute_spectral_metrics(self.model, self.config.spectral)
+
+
+def save_epoch_spectral_artifacts(snapshot: Any, epoch: int, artifacts_dir: Any, mlflow_module: Any = None):
+    """JSON half of `BaseTrainer._save_epoch_spectral_artifacts` (training/base.py:453-511): writes
+    `spectral/json/spectral_epoch_%04d.json` with the reference's layout -- epoch, timestamp, aggregated_metrics and per
+    distribution name / matrix_type / singular_values (already truncated to the tracker's max_singular_values) /
+    metrics -- and logs it under `spectral/json` when an mlflow module is given.  The per-layer histogram PNGs of the
+    reference (:513-567) are plotting: out of scope.  Returns the path."""
+    import json
+    from pathlib import Path
+
+    json_dir = Path(artifacts_dir) / "spectral" / "json"
+    json_dir.mkdir(parents=True, exist_ok=True)
+    epoch_data = {
+        "epoch": epoch,
+        "timestamp": snapshot.timestamp,
+        "aggregated_metrics": snapshot.aggregated_metrics,
+        "distributions": [
+            {"name": d.name, "matrix_type": d.matrix_type, "singular_values": np.asarray(d.singular_values).tolist(), "metrics": d.metrics}
+            for d in snapshot.distributions
+        ],
+    }
+    json_path = json_dir / f"spectral_epoch_{epoch:04d}.json"
+    with open(json_path, "w") as f:
+        json.dump(epoch_data, f, indent=2)
+    if mlflow_module is not None:
+        mlflow_module.log_artifact(str(json_path), artifact_path="spectral/json")
+    return json_path

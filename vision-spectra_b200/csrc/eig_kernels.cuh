@@ -250,3 +250,5 @@ __global__ void __launch_bounds__(1024)
 }
 
 }  // namespace vsp
+
+#include "refine_cluster.cuh"  // needs RefinePool

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <climits>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -87,6 +88,9 @@ struct ShapeClass {
     int64_t refine_off;           // byte offset of the pool in the refine region
     int64_t refine_items_off;     // byte offset of the slot -> item table
     int refine_counter;           // index of this class's slot counter
+    int refine_B;                 // CTAs per cluster of the re-solve (0: one-CTA kernel)
+    int refine_kmax;              // largest contraction length of the class
+    int refine_xs_cap;            // doubles of shared memory for a CTA's share of X
 };
 
 int validate(int32_t count, const int32_t* rows, const int32_t* cols, const int64_t* ld) {
@@ -376,6 +380,23 @@ static int plan_layout(vsp_plan* p, int32_t count, const int32_t* rows, const in
             for (int s = c.begin; s < c.begin + c.count; ++s)
                 kn = std::max<int64_t>(kn, (int64_t)p->items[s].kdim * p->items[s].n);
             c.refine_slot_doubles = round_up64(kn, 4);
+            {   // cluster re-solve (refine_cluster.cuh): B CTAs per flagged matrix; VSP_REFINE_OLD=1 keeps the one-CTA kernel
+                static const bool old_refine = std::getenv("VSP_REFINE_OLD") != nullptr;
+                int kmax = 0;
+                int64_t min_share = INT64_MAX;
+                const int B = c.n <= 256 ? 4 : kRcMaxCluster;
+                for (int s = c.begin; s < c.begin + c.count; ++s) {
+                    kmax = std::max(kmax, p->items[s].kdim);
+                    min_share = std::min<int64_t>(min_share, (int64_t)((c.n + B - 1) / B) * p->items[s].kdim);
+                }
+                c.refine_B = (old_refine || c.n < 16) ? 0 : B;
+                c.refine_kmax = kmax;
+                // a CTA's share of X stays in shared memory when it is small (the square matrices of ViT-Tiny: 74 KB),
+                // which leaves room for bisection CTAs on the same SM; larger shares work from the L2-resident pool
+                c.refine_xs_cap = (min_share <= 12288) ? 12288 : 0;
+                if (c.refine_B > 0)
+                    c.refine_slot_doubles = round_up64(refine_cluster_slot_doubles(kmax, c.n, c.refine_B), 4);
+            }
             // pool buffers = CTAs of the re-solve launch (1024 threads: one per SM); more flagged items than
             // buffers are served in rounds, so the pool never limits how many items can be re-solved
             c.refine_slots = std::min(c.count, std::max(4, std::min(c.count / 8, 2 * 148)));
@@ -616,7 +637,33 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
             const int xs_doubles = (int)((rsm - fixed) / sizeof(double));
             VSP_CUDA(cudaEventRecord(p->ev_fork, st));
             VSP_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
-            if (p->dtype == VSP_F32) {
+            if (c.refine_B > 0) {
+                const int B = c.refine_B, Kpad = round_up(c.refine_kmax, 4), nloc = (c.n + B - 1) / B;
+                const size_t smem_d = std::max(refine_cluster_fixed_doubles(c.npad, Kpad, nloc) + (size_t)c.refine_xs_cap,
+                                               refine_cluster_tail_doubles(c.npad));
+                const size_t csmem = smem_d * sizeof(double);
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)(B * c.refine_slots));
+                cfg.blockDim = dim3(kRcThreads);
+                cfg.dynamicSmemBytes = csmem;
+                cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = (unsigned)B;
+                attr[0].val.clusterDim.y = 1;
+                attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                if (p->dtype == VSP_F32) {
+                    VSP_CUDA(cudaFuncSetAttribute(refine_cluster_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(csmem, 48 * 1024)));
+                    VSP_CUDA(cudaLaunchKernelEx(&cfg, refine_cluster_kernel<float>, (const ItemDesc*)p->d_items, gate, pool, c.npad, Kpad, nloc,
+                                                c.refine_xs_cap, p->opts, d_sv, d_records, d_dist));
+                } else {
+                    VSP_CUDA(cudaFuncSetAttribute(refine_cluster_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(csmem, 48 * 1024)));
+                    VSP_CUDA(cudaLaunchKernelEx(&cfg, refine_cluster_kernel<double>, (const ItemDesc*)p->d_items, gate, pool, c.npad, Kpad, nloc,
+                                                c.refine_xs_cap, p->opts, d_sv, d_records, d_dist));
+                }
+            } else if (p->dtype == VSP_F32) {
                 VSP_CUDA(cudaFuncSetAttribute(refine_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
                 refine_kernel<float><<<c.refine_slots, 1024, rsm, st>>>(p->d_items, gate, pool, c.npad, xs_doubles, p->opts, d_sv, d_records, d_dist);
             } else {
@@ -626,7 +673,8 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
             g_launches++;
             t_timer.tick("refine", st);
             VSP_CUDA(cudaGetLastError());
-            bst = p->side;
+            static const bool serial_refine = std::getenv("VSP_REFINE_SERIAL") != nullptr;  // experiments: no overlap
+            bst = serial_refine ? st : p->side;
         }
         const int bthreads = bisect_threads(c.n);
         if (bthreads <= 128)

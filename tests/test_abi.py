@@ -63,7 +63,8 @@ def test_shape_validation_and_layout_queries(lib):
     tri = sum(n * (n + 1) // 2 + 2 * n for n in (32, 32, 32, 768)) * 8
     planes = sum(6 * n * k for n, k in ((32, 32), (32, 128), (32, 128), (768, 3072)))
     pool = 3 * 128 * 32 * 8 + 768 * 3072 * 8
-    assert tri + planes + pool <= ws <= tri + planes + pool + 256 * 1024
+    # (+ band outputs, exchange buffers of the cluster re-solve, rounding flags, alignment: within 10 % + 1 MB)
+    assert tri + planes + pool <= ws <= 1.1 * (tri + planes + pool) + (1 << 20)
     offs = np.zeros(5, np.int64)
     assert lib.vsp_sv_offsets(4, nat.p32(rows), nat.p32(cols), nat.p64(offs)) == 0
     assert offs.tolist() == [0, 32, 64, 96, 864]

@@ -307,8 +307,9 @@ SCENARIOS = {  # reference table experiments/run_spectral_analysis.py:145-236: (
 SEEDS = (42, 142, 242)  # run_spectral_analysis.py:706
 
 
-def _device_time(fn, sync_all, steps: int, warmup: int = 2) -> float:
-    """ms per call of fn(), CUDA events on the current stream, barrier + synchronize on both sides, max over ranks."""
+def _device_time(fn, sync_all, steps: int, warmup: int = 2, collective: bool = True) -> float:
+    """ms per call of fn(), CUDA events on the current stream, barrier + synchronize on both sides; max over ranks when
+    every rank takes part (`collective`), this rank's own time for the rank-0-only entries."""
     import torch
     import torch.distributed as dist
 
@@ -322,7 +323,7 @@ def _device_time(fn, sync_all, steps: int, warmup: int = 2) -> float:
     e1.record()
     sync_all()
     ms = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda", dtype=torch.float64)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    if collective and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     return float(ms.item())
 
@@ -387,7 +388,7 @@ def extra_scenario(eng, dev, key: str, sync_all, steps: int = 3) -> dict:
     runner = SweepRunner(eng, lay)
     g = torch.Generator(device=dev).manual_seed(1000 + ord(key))
     arenas = [torch.randn(lay.arena_elems, generator=g, device=dev, dtype=torch.float32) * 0.02 for _ in range(epochs * len(SEEDS))]
-    ms = _device_time(lambda: runner.run_device(arenas, want_sv=True), sync_all, steps)
+    ms = _device_time(lambda: runner.run_device(arenas, want_sv=True), sync_all, steps, collective=False)
     n = len(arenas) * lay.matrices
     return {"workload": f"Scenario {key}: ViT {d}d/{depth}L, {epochs} epochs x {len(SEEDS)} seeds", "matrices": n, "ms": ms,
             "matrices_per_s": n / (ms / 1e3), "per_rank": True}
@@ -546,7 +547,9 @@ def run_b200_arm(args) -> None:
         saved = os.dup(1)
         os.dup2(2, 1)
         try:
-            dist.init_process_group("nccl", device_id=dev)
+            import datetime
+
+            dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))  # fail fast, never hang a box
             dist.barrier(device_ids=[local])
             torch.cuda.synchronize(dev)
         finally:

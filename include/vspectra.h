@@ -79,8 +79,20 @@ typedef struct vsp_opts {
                           eigenvalues s^2, normalized_sv s/s_0, cumulative_variance cumsum(s^2)/sum(s^2) -- i.e.
                           SpectralTracker's max_singular_values truncation (spectral.py:683-692) done on the
                           device: vsp_plan_execute_dist.  0 / -1: off */
-    int32_t reserved[2];
+    int32_t clauset;   /* 1: also run the Clauset-Shalizi-Newman x_min scan on the eigenvalue spectrum (BASELINE
+                          north_star stage 3; the reference has no such scan -- SURVEY D1 -- so this output is an
+                          extra with its own oracle, oracle/spectral_oracle.py: clauset_xmin_scan): for EVERY
+                          candidate cutoff x_min = lambda_(k) the continuous MLE alpha = 1 + t / sum ln(lambda_i / x_min)
+                          over the t eigenvalues >= x_min and the Kolmogorov-Smirnov distance of the fitted tail; the
+                          cutoff with the smallest distance wins.  Output through vsp_plan_execute_dist.  0: off */
+    int32_t reserved[1];
 } vsp_opts;
+
+/* Doubles per matrix of the auxiliary output of vsp_plan_execute_dist: 4 * dist_k (rows singular_values, eigenvalues,
+ * normalized_sv, cumulative_variance) followed, when opts.clauset is set, by 8 doubles
+ * { alpha, x_min, ks_distance, x_min index (0 = largest eigenvalue), tail count t, 0, 0, 0 } (NaN / -1 when fewer
+ * than 8 positive eigenvalues). */
+#define VSP_AUX_STRIDE(dist_k, clauset) (4 * ((dist_k) > 0 ? (dist_k) : 0) + ((clauset) ? 8 : 0))
 
 /* One result record per matrix: 64 bytes, the unit that is gathered across GPUs. */
 typedef struct vsp_record {
@@ -138,10 +150,11 @@ int vsp_plan_execute(vsp_plan* plan, const void* const* d_ptrs, double* d_sv,
                      vsp_record* d_records, void* d_workspace, int64_t workspace_bytes,
                      void* stream);
 
-/* vsp_plan_execute for plans created with opts.dist_k > 0: additionally fills
- *   d_dist      DEVICE f64 [count][4][dist_k]: per matrix (batch order) the rows singular_values, eigenvalues,
- *               normalized_sv, cumulative_variance, truncated to dist_k entries; entries beyond min(rows, cols)
- *               and every entry of a matrix with non-finite input are NaN.
+/* vsp_plan_execute for plans created with opts.dist_k > 0 and / or opts.clauset: additionally fills
+ *   d_dist      DEVICE f64 [count][VSP_AUX_STRIDE(dist_k, clauset)]: per matrix (batch order) the rows
+ *               singular_values, eigenvalues, normalized_sv, cumulative_variance, truncated to dist_k entries (entries
+ *               beyond min(rows, cols) and every entry of a matrix with non-finite input are NaN), then the
+ *               Clauset block.
  * d_sv may be NULL when the plan has want_sv == 0: a tracker epoch then moves 4 dist_k values per matrix
  * instead of min(rows, cols). */
 int vsp_plan_execute_dist(vsp_plan* plan, const void* const* d_ptrs, double* d_sv,

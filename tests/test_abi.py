@@ -108,6 +108,6 @@ def test_torch_extension_loads_and_registers_the_op():
 
     ops = nat.load_torch_ext()
     schema = str(torch.ops.vision_spectra_b200.analyze_batch.default._schema)
-    assert "Tensor[] matrices" in schema and "int hill_k=-1" in schema and "bool want_sv=True" in schema and "int dist_k=0" in schema
+    assert "Tensor[] matrices" in schema and "int hill_k=-1" in schema and "bool want_sv=True" in schema and "int dist_k=0" in schema and "bool clauset=False" in schema
     with pytest.raises((RuntimeError, NotImplementedError)):
-        ops.analyze_batch([torch.zeros(4, 4)], -1, -1, -1, True, 0)
+        ops.analyze_batch([torch.zeros(4, 4)], -1, -1, -1, True, 0, False)

@@ -576,3 +576,26 @@ def test_device_distribution_arrays_and_tracker_truncation(engine):
     for d in snap.distributions[:3]:
         w = dict((n_, p_) for n_, p_ in model.named_parameters())
         assert d.singular_values[0] >= d.singular_values[-1] > 0 and abs(d.normalized_sv[0] - 1.0) < 1e-15
+
+
+def test_clauset_xmin_scan_matches_its_oracle(engine):
+    """North-star stage 3 extra: the Clauset x_min scan (every candidate cutoff in parallel: MLE alpha + KS distance).
+    The reference has no such scan, so this is checked against the restatement of the published algorithm
+    in oracle/spectral_oracle.py: integer outputs (x_min index, tail count) exact, alpha / x_min / D to 1e-6."""
+    from vision_spectra_b200.metrics.spectral import clauset_power_law_fit
+
+    rng = np.random.default_rng(404)
+    host = [trunc_normal(rng, (192, 192)), trunc_normal(rng, (768, 192)), trunc_normal(rng, (33, 70)),
+            build_case("powerlaw:100:1.0:f64"), build_case("powerlaw:100:2.0:f64"), build_case("sgd:192x192"), trunc_normal(rng, (5, 9))]
+    out: list = []
+    engine.analyze([torch.from_numpy(np.ascontiguousarray(w)).cuda() for w in host], want_sv=False, clauset_out=out)
+    for w, c in zip(host, out):
+        ref = orc.clauset_xmin_scan(w)
+        assert (c["xmin_index"], c["tail_count"]) == (ref["xmin_index"], ref["tail_count"]), (w.shape, c, ref)
+        if ref["tail_count"] < 0:
+            assert np.isnan(c["alpha"])
+            continue
+        for k in ("alpha", "xmin", "ks_distance"):
+            assert abs(c[k] - ref[k]) <= 1e-6 * abs(ref[k]), (w.shape, k, c[k], ref[k])
+    one = clauset_power_law_fit(torch.from_numpy(host[0]).cuda())
+    assert one["tail_count"] == out[0]["tail_count"] and abs(one["alpha"] - out[0]["alpha"]) < 1e-12

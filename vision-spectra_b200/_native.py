@@ -45,18 +45,25 @@ class VspOpts(ctypes.Structure):
         ("want_sv", c_int32),
         ("refine", c_int32),
         ("dist_k", c_int32),
-        ("reserved", c_int32 * 2),
+        ("clauset", c_int32),
+        ("reserved", c_int32 * 1),
     ]
 
     @classmethod
-    def make(cls, fit_range=None, hill_k=None, want_sv=True, refine=None, dist_k=0):
+    def make(cls, fit_range=None, hill_k=None, want_sv=True, refine=None, dist_k=0, clauset=False):
         o = cls()
         o.fit_start, o.fit_end = (-1, -1) if fit_range is None else (int(fit_range[0]), int(fit_range[1]))
         o.hill_k = -1 if hill_k is None else int(hill_k)
         o.want_sv = 1 if want_sv else 0
         o.refine = -1 if refine is None else int(bool(refine))
         o.dist_k = max(0, int(dist_k or 0))
+        o.clauset = 1 if clauset else 0
         return o
+
+
+def aux_stride(dist_k: int, clauset: bool) -> int:
+    """VSP_AUX_STRIDE of include/vspectra.h: doubles per matrix of the auxiliary output."""
+    return 4 * max(0, int(dist_k or 0)) + (8 if clauset else 0)
 
 
 class NativeError(RuntimeError):

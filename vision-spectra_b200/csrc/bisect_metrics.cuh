@@ -415,12 +415,14 @@ struct MetricOut {
 // (spectral.py:545-557), rows sv | sv^2 | sv / sv_0 | cumsum(sv^2) / sum(sv^2) of a [4][dist_k] block; NaN beyond n.
 template <class Ctx>
 VSP_DEV MetricOut spectral_metrics(Ctx& ctx, double* lam, int n, double scale, int flags,
-                                   int fit_start, int fit_end, int hill_k, double* sv, double* dist = nullptr, int dist_k = 0) {
+                                   int fit_start, int fit_end, int hill_k, double* sv, double* dist = nullptr, int dist_k = 0,
+                                   double* clauset = nullptr) {
     MetricOut out;
     const double nan = NAN;
     if (dist_k <= 0) dist = nullptr;
     if (dist)  // NaN everywhere first: the failure paths below and the entries beyond n keep it
         for (int i = ctx.tid; i < 4 * dist_k; i += ctx.nthreads) dist[i] = nan;
+    if (clauset && ctx.tid < 8) clauset[ctx.tid] = (ctx.tid == 3 || ctx.tid == 4) ? -1.0 : ((ctx.tid < 3) ? nan : 0.0);
     out.metrics[0] = out.metrics[1] = out.metrics[2] = out.metrics[3] = nan;
     out.m = 0;
     out.start = out.end = out.k = -1;
@@ -557,6 +559,49 @@ VSP_DEV MetricOut spectral_metrics(Ctx& ctx, double* lam, int n, double scale, i
         }
     } else {
         out.status |= VSP_ST_FEW_SV;
+    }
+
+    // ---- Clauset-Shalizi-Newman x_min scan over the eigenvalue spectrum (opt-in; no counterpart in the reference).
+    // Candidate cutoff k (0-based from the SMALLEST eigenvalue, k <= m - 2): tail = lam[k..m), t = m - k,
+    // alpha_k = 1 + t / sum_{i >= k} ln(lam_i / lam_k), D_k = max_j max(|j/t - P(x_j)|, |(j-1)/t - P(x_j)|) over the
+    // tail in ascending order, P(x) = 1 - (x / lam_k)^(1 - alpha_k).  All candidates in parallel (one per thread, cyclic),
+    // the smallest D wins (ties: the smaller cutoff).  lam[] is overwritten by ln lam (nothing reads it afterwards).
+    if (clauset && m >= 8) {
+        ctx.sync();
+        for (int i = ctx.tid; i < n; i += ctx.nthreads) lam[i] = log(lam[i]);
+        ctx.sync();
+        double bestD = 1e300, bestA = nan;
+        int bestK = -1;
+        for (int k = ctx.tid; k <= m - 2; k += ctx.nthreads) {
+            const double lk = lam[k];
+            const int t = m - k;
+            double sl = 0.0;
+            for (int i = k; i < m; ++i) sl += lam[i] - lk;
+            if (!(sl > 0.0)) continue;  // a flat tail has no power-law fit
+            const double a = 1.0 + (double)t / sl;
+            const double e = 1.0 - a, it = 1.0 / (double)t;
+            double D = 0.0;
+            for (int j = 0; j < t; ++j) {
+                const double P = 1.0 - exp(e * (lam[k + j] - lk));
+                D = fmax(D, fmax(fabs((double)(j + 1) * it - P), fabs((double)j * it - P)));
+            }
+            if (D < bestD) {
+                bestD = D;
+                bestA = a;
+                bestK = k;
+            }
+        }
+        // arg-min over the threads: smallest D, then smallest cutoff
+        const double gD = ctx.min(bestD);
+        const int cand = (bestD == gD && bestK >= 0) ? bestK : 0x7fffffff;
+        const int gK = -ctx.max_i(-cand);
+        if (bestK == gK && gK != 0x7fffffff) {
+            clauset[0] = bestA;
+            clauset[1] = exp(lam[gK]) / scale;     // x_min in the units of sigma^2
+            clauset[2] = gD;
+            clauset[3] = (double)(m - 1 - gK);     // index in DESCENDING order (0 = largest eigenvalue)
+            clauset[4] = (double)(m - gK);         // tail count
+        }
     }
     return out;
 }

@@ -129,8 +129,9 @@ __global__ void __launch_bounds__(MAXT, MINB) bisect_metrics_kernel(const ItemDe
     }
     iters = ctx.max_i(iters);  // barrier: lam[] complete
     double* sv = (opts.want_sv != 0 && sv_out != nullptr) ? sv_out + it.sv_off : nullptr;
-    double* dist = (dist_out != nullptr && opts.dist_k > 0) ? dist_out + (int64_t)it.item * 4 * opts.dist_k : nullptr;
-    const MetricOut mo = spectral_metrics(ctx, lam, n, scale, flags, opts.fit_start, opts.fit_end, opts.hill_k, sv, dist, opts.dist_k);
+    double* aux = dist_out != nullptr ? dist_out + (int64_t)it.item * VSP_AUX_STRIDE(opts.dist_k, opts.clauset) : nullptr;
+    const MetricOut mo = spectral_metrics(ctx, lam, n, scale, flags, opts.fit_start, opts.fit_end, opts.hill_k, sv, aux, opts.dist_k,
+                                          (aux != nullptr && opts.clauset) ? aux + VSP_AUX_STRIDE(opts.dist_k, 0) : nullptr);
     if (ctx.tid == 0) {
         vsp_record r;
         r.item = it.item;
@@ -227,8 +228,9 @@ __global__ void __launch_bounds__(1024)
     int iters = gk_singular_values(ctx, dq, eq, n, de, lam);
     iters = ctx.max_i(iters);  // barrier: lam[] complete
     double* sv = (opts.want_sv != 0 && sv_out != nullptr) ? sv_out + it.sv_off : nullptr;
-    double* dist = (dist_out != nullptr && opts.dist_k > 0) ? dist_out + (int64_t)it.item * 4 * opts.dist_k : nullptr;
-    const MetricOut mo = spectral_metrics(ctx, lam, n, sc * sc, 0, opts.fit_start, opts.fit_end, opts.hill_k, sv, dist, opts.dist_k);
+    double* aux = dist_out != nullptr ? dist_out + (int64_t)it.item * VSP_AUX_STRIDE(opts.dist_k, opts.clauset) : nullptr;
+    const MetricOut mo = spectral_metrics(ctx, lam, n, sc * sc, 0, opts.fit_start, opts.fit_end, opts.hill_k, sv, aux, opts.dist_k,
+                                          (aux != nullptr && opts.clauset) ? aux + VSP_AUX_STRIDE(opts.dist_k, 0) : nullptr);
     if (ctx.tid == 0) {
         vsp_record r;
         r.item = it.item;

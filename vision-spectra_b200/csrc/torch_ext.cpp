@@ -1,14 +1,14 @@
 // torch_ext.cpp -- PyTorch extension layer of the drop-in boundary.
 //
 //   torch.ops.vision_spectra_b200.analyze_batch(Tensor[] matrices, int fit_start, int fit_end, int hill_k, bool want_sv,
-//                                               int dist_k) -> (Tensor records, Tensor singular_values, Tensor dist)
+//                                               int dist_k, bool clauset) -> (Tensor records, Tensor singular_values, Tensor aux)
 //
 // One ragged batch of 2-D CUDA tensors (one dtype, float32 or float64, unit column stride; q/k/v may be row-block
 // views of a fused qkv buffer) through the C-ABI of include/vspectra.h: replaces the reference's per-matrix loop
 // experiments/run_spectral_analysis.py:323-336 / training/base.py:399-405.  Asynchronous on the CURRENT stream of the
 // tensors' device, under a device guard; inputs are borrowed; the outputs -- records uint8 [count, 64] (vsp_record) and
 // singular values float64 [sum min(rows, cols)], descending per matrix, and with dist_k > 0 the truncated distribution
-// arrays float64 [count, 4, dist_k] (vspectra.h: vsp_plan_execute_dist) -- and the workspace are ATen allocations, so
+// arrays / Clauset block float64 [count, VSP_AUX_STRIDE] (vspectra.h: vsp_plan_execute_dist) -- and the workspace are ATen allocations, so
 // the caching allocator's stream ordering keeps them alive exactly as long as the kernels need them.  No host
 // synchronisation, no CPU fallback: a non-CUDA tensor is an error.
 //
@@ -71,7 +71,7 @@ PlanCache& cache() {
 }
 
 std::tuple<at::Tensor, at::Tensor, at::Tensor> analyze_batch_cuda(at::TensorList matrices, int64_t fit_start, int64_t fit_end,
-                                                                  int64_t hill_k, bool want_sv, int64_t dist_k) {
+                                                                  int64_t hill_k, bool want_sv, int64_t dist_k, bool clauset) {
     const int64_t count = (int64_t)matrices.size();
     TORCH_CHECK(count > 0, "analyze_batch: empty batch");
     const at::Tensor& first = matrices[0];
@@ -104,13 +104,14 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor> analyze_batch_cuda(at::TensorList
     opts.want_sv = want_sv ? 1 : 0;
     opts.refine = -1;
     opts.dist_k = dist_k > 0 ? (int32_t)dist_k : 0;
+    opts.clauset = clauset ? 1 : 0;
     const int32_t dtype = st == at::kFloat ? VSP_F32 : VSP_F64;
 
     std::string key;
     key.reserve(64 + 16 * (size_t)count);
     auto put = [&key](const void* p, size_t n) { key.append(reinterpret_cast<const char*>(p), n); };
-    const int64_t head[8] = {(int64_t)first.device().index(), (int64_t)(uintptr_t)stream, dtype, fit_start, fit_end, hill_k, want_sv ? 1 : 0,
-                             opts.dist_k};
+    const int64_t head[9] = {(int64_t)first.device().index(), (int64_t)(uintptr_t)stream, dtype, fit_start, fit_end, hill_k, want_sv ? 1 : 0,
+                             opts.dist_k, opts.clauset};
     put(head, sizeof head);
     put(rows.data(), sizeof(int32_t) * rows.size());
     put(cols.data(), sizeof(int32_t) * cols.size());
@@ -122,10 +123,11 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor> analyze_batch_cuda(at::TensorList
     at::Tensor sv = at::empty({want_sv ? sv_total : 0}, first.options().dtype(at::kDouble));
     const int64_t ws_bytes = vsp_plan_workspace_bytes(plan);
     at::Tensor ws = at::empty({ws_bytes}, bytes);
-    at::Tensor dist = at::empty({opts.dist_k > 0 ? count : 0, 4, opts.dist_k}, first.options().dtype(at::kDouble));
+    const bool aux = opts.dist_k > 0 || opts.clauset > 0;
+    at::Tensor dist = at::empty({aux ? count : 0, (int64_t)VSP_AUX_STRIDE(opts.dist_k, opts.clauset)}, first.options().dtype(at::kDouble));
     double* svp = want_sv ? sv.data_ptr<double>() : nullptr;
     vsp_record* recp = reinterpret_cast<vsp_record*>(records.data_ptr());
-    const int rc = opts.dist_k > 0
+    const int rc = aux
                        ? vsp_plan_execute_dist(plan, ptrs.data(), svp, recp, dist.data_ptr<double>(), ws.data_ptr(), ws_bytes, stream)
                        : vsp_plan_execute(plan, ptrs.data(), svp, recp, ws.data_ptr(), ws_bytes, stream);
     TORCH_CHECK(rc == VSP_OK, "vsp_plan_execute failed: ", vsp_error_string(rc), " (", vsp_last_cuda_error(), ")");
@@ -135,7 +137,7 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor> analyze_batch_cuda(at::TensorList
 }  // namespace
 
 TORCH_LIBRARY(vision_spectra_b200, m) {
-    m.def("analyze_batch(Tensor[] matrices, int fit_start=-1, int fit_end=-1, int hill_k=-1, bool want_sv=True, int dist_k=0) -> (Tensor, Tensor, Tensor)");
+    m.def("analyze_batch(Tensor[] matrices, int fit_start=-1, int fit_end=-1, int hill_k=-1, bool want_sv=True, int dist_k=0, bool clauset=False) -> (Tensor, Tensor, Tensor)");
 }
 
 TORCH_LIBRARY_IMPL(vision_spectra_b200, CUDA, m) { m.impl("analyze_batch", &analyze_batch_cuda); }

@@ -284,7 +284,10 @@ static int plan_layout(vsp_plan* p, int32_t count, const int32_t* rows, const in
         p->opts.want_sv = -1;
         p->opts.refine = -1;
         p->opts.dist_k = 0;
+        p->opts.clauset = 0;
     }
+    if (p->opts.clauset != 1) p->opts.clauset = 0;
+    if (p->opts.dist_k < 0) p->opts.dist_k = 0;
     // caller-order SV offsets
     std::vector<int64_t> sv_off(count + 1, 0);
     for (int i = 0; i < count; ++i) sv_off[i + 1] = sv_off[i] + std::min(rows[i], cols[i]);
@@ -463,7 +466,7 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
     if (p->count == 0) return VSP_OK;
     if (!d_ptrs || !d_records || !d_workspace) return VSP_E_ARG;
     if (p->opts.want_sv != 0 && !d_sv) return VSP_E_ARG;
-    if (p->opts.dist_k > 0 && !d_dist) return VSP_E_ARG;  // a distribution plan needs vsp_plan_execute_dist
+    if ((p->opts.dist_k > 0 || p->opts.clauset > 0) && !d_dist) return VSP_E_ARG;  // such a plan needs vsp_plan_execute_dist
     // align the workspace to 256 bytes inside the caller's buffer
     uintptr_t base = reinterpret_cast<uintptr_t>(d_workspace);
     uintptr_t aligned = (base + 255) & ~uintptr_t(255);
@@ -761,7 +764,7 @@ int vsp_plan_execute(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vsp_r
 
 int vsp_plan_execute_dist(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vsp_record* d_records, double* d_dist,
                           void* d_workspace, int64_t workspace_bytes, void* stream) {
-    if (!p || p->opts.dist_k <= 0 || !d_dist) return VSP_E_ARG;
+    if (!p || (p->opts.dist_k <= 0 && p->opts.clauset <= 0) || !d_dist) return VSP_E_ARG;
     return execute_impl(p, d_ptrs, d_sv, d_records, d_workspace, workspace_bytes, stream, nullptr, d_dist);
 }
 

@@ -43,7 +43,7 @@ class BatchResult:
         self.sv = sv  # float64 [sum n] or None
         self.sv_offsets = sv_offsets  # int64 [count+1]
         self.count = count
-        self.dist = dist  # float64 [count, 4, dist_k] or None: sv | sv^2 | sv/sv_0 | cumulative variance, truncated
+        self.dist = dist  # float64 [count, VSP_AUX_STRIDE] or None: 4 x dist_k distribution rows, then the Clauset block
 
     def dist_host(self) -> np.ndarray | None:
         return None if self.dist is None else self.dist.cpu().numpy()
@@ -108,7 +108,7 @@ class SpectraEngine:
 
     # ------------------------------------------------------------------ plans
     def _plan(self, rows, cols, ld, dtype: int, opts: nat.VspOpts) -> Plan:
-        key = (rows.tobytes(), cols.tobytes(), ld.tobytes(), dtype, opts.fit_start, opts.fit_end, opts.hill_k, opts.want_sv, opts.refine, opts.dist_k)
+        key = (rows.tobytes(), cols.tobytes(), ld.tobytes(), dtype, opts.fit_start, opts.fit_end, opts.hill_k, opts.want_sv, opts.refine, opts.dist_k, opts.clauset)
         plan = self._plans.get(key)
         if plan is not None:
             self._plans.move_to_end(key)
@@ -142,6 +142,7 @@ class SpectraEngine:
         hill_k: int | None = None,
         want_sv: bool = True,
         dist_k: int = 0,
+        clauset: bool = False,
     ) -> BatchResult:
         """Launch the three stages for 2-D CUDA tensors of ONE dtype (float32 or
         float64) with unit column stride.  Asynchronous on the current stream;
@@ -160,10 +161,10 @@ class SpectraEngine:
                     raise ValueError("analyze_device: tensors must be on the engine device")
             fs, fe = (-1, -1) if fit_range is None else (int(fit_range[0]), int(fit_range[1]))
             records, sv, dist = nat.load_torch_ext().analyze_batch(list(tensors), fs, fe, -1 if hill_k is None else int(hill_k),
-                                                                   bool(want_sv), int(dist_k or 0))
+                                                                   bool(want_sv), int(dist_k or 0), bool(clauset))
             offs = np.zeros(count + 1, np.int64)
             np.cumsum([min(t.shape) for t in tensors], out=offs[1:])
-            return BatchResult(records.view(-1), sv if want_sv else None, offs, count, dist if dist_k else None)
+            return BatchResult(records.view(-1), sv if want_sv else None, offs, count, dist if (dist_k or clauset) else None)
         rows = np.empty(count, np.int32)
         cols = np.empty(count, np.int32)
         ld = np.empty(count, np.int64)
@@ -177,7 +178,7 @@ class SpectraEngine:
                 raise ValueError("analyze_device: overlapping rows (stride(0) < cols)")
             ptrs[i] = t.data_ptr()
         dtype = nat.VSP_F32 if dt == torch.float32 else nat.VSP_F64
-        return self.analyze_raw(ptrs, rows, cols, ld, dtype, fit_range, hill_k, want_sv, dist_k=dist_k)
+        return self.analyze_raw(ptrs, rows, cols, ld, dtype, fit_range, hill_k, want_sv, dist_k=dist_k, clauset=clauset)
 
     def analyze_raw(
         self,
@@ -194,6 +195,7 @@ class SpectraEngine:
         out_records: torch.Tensor | None = None,
         out_sv: torch.Tensor | None = None,
         dist_k: int = 0,
+        clauset: bool = False,
     ) -> BatchResult:
         """Table form of analyze_device: `ptrs` is a uint64 array of device addresses,
         rows/cols int32, ld int64 (elements).  The caller keeps the memory alive until
@@ -202,7 +204,7 @@ class SpectraEngine:
         count = int(len(ptrs))
         ptrs = np.ascontiguousarray(ptrs, dtype=np.uint64)
         if plan is None:
-            plan = self.make_plan(rows, cols, ld, dtype, fit_range, hill_k, want_sv, dist_k)
+            plan = self.make_plan(rows, cols, ld, dtype, fit_range, hill_k, want_sv, dist_k, clauset)
         if plan.handle is None:
             raise nat.NativeError("analyze_raw: the plan has been closed")
         ws_bytes = self.lib.vsp_plan_workspace_bytes(plan.handle)
@@ -226,8 +228,8 @@ class SpectraEngine:
             stream,
         )
         dist = None
-        if dist_k:
-            dist = torch.empty((count, 4, int(dist_k)), dtype=torch.float64, device=self.device)
+        if dist_k or clauset:
+            dist = torch.empty((count, nat.aux_stride(dist_k, clauset)), dtype=torch.float64, device=self.device)
             with torch.cuda.device(self.device):
                 nat.check(self.lib.vsp_plan_execute_dist(*args[:4], dist.data_ptr(), *args[4:]), "vsp_plan_execute_dist")
             offs = np.zeros(count + 1, np.int64)
@@ -244,10 +246,11 @@ class SpectraEngine:
         np.cumsum(np.minimum(rows, cols), out=offs[1:])
         return BatchResult(records, sv, offs, count)
 
-    def make_plan(self, rows, cols, ld, dtype: int, fit_range=None, hill_k=None, want_sv: bool = True, dist_k: int = 0) -> Plan:
+    def make_plan(self, rows, cols, ld, dtype: int, fit_range=None, hill_k=None, want_sv: bool = True, dist_k: int = 0,
+                  clauset: bool = False) -> Plan:
         """Validated, device-resident shape table for a batch (cached per engine; the returned `Plan` stays
         valid for as long as the caller holds it, whatever the cache evicts)."""
-        opts = nat.VspOpts.make(fit_range, hill_k, want_sv, dist_k=dist_k)
+        opts = nat.VspOpts.make(fit_range, hill_k, want_sv, dist_k=dist_k, clauset=clauset)
         return self._plan(nat.i32(rows), nat.i32(cols), nat.i64(ld), dtype, opts)
 
     # ----------------------------------------------------------------- host path
@@ -284,6 +287,7 @@ class SpectraEngine:
         want_sv: bool = True,
         dist_k: int = 0,
         dist_out: list | None = None,
+        clauset_out: list | None = None,
     ) -> tuple[list[dict[str, float]], list[np.ndarray | None], np.ndarray]:
         """Analyse a ragged list of matrices (torch tensors on any device or NumPy
         arrays, any float dtype).  Returns (metrics dicts, singular-value arrays,
@@ -293,7 +297,9 @@ class SpectraEngine:
 
         `dist_k > 0` asks for the device-computed distribution arrays (spectral.py:545-557) truncated to `dist_k`
         entries (SpectralTracker's max_singular_values); they are appended to the list `dist_out`, one [4, min(n, dist_k)]
-        array per matrix (None where the reference returns no distribution).
+        array per matrix (None where the reference returns no distribution).  Passing a list as `clauset_out` switches
+        on the Clauset-Shalizi-Newman x_min scan (an extra: the reference has none) and fills it with one dict per
+        matrix: alpha, xmin, ks_distance, xmin_index (0 = largest eigenvalue), tail_count.
 
         float32 / float16 / bfloat16 inputs are analysed from their (exactly widened) float32 values; float64,
         integer and extended-precision inputs from float64, as the reference's `np.asarray(w, dtype=np.float64)`
@@ -343,16 +349,22 @@ class SpectraEngine:
         for tdt, lst in groups.items():
             if lst:
                 lst.sort(key=lambda p: p[0])
-                res = self.analyze_device([t for _, t in lst], fit_range, hill_k, want_sv, dist_k)
+                res = self.analyze_device([t for _, t in lst], fit_range, hill_k, want_sv, dist_k, clauset_out is not None)
                 pending.append((lst, res))
         dists: list = [None] * count
+        clausets: list = [None] * count
         for lst, res in pending:
             rec = res.records_host()
             sv = res.sv_host()
             dh = res.dist_host()
+            dk = max(0, int(dist_k or 0))
             for j, (i, t) in enumerate(lst):
-                if dh is not None and not (int(rec[j]["status"]) & nat.ST_NONFINITE):
-                    dists[i] = dh[j][:, : min(int(dist_k), min(t.shape))].copy()
+                if dh is not None and dk and not (int(rec[j]["status"]) & nat.ST_NONFINITE):
+                    dists[i] = dh[j][: 4 * dk].reshape(4, dk)[:, : min(dk, min(t.shape))].copy()
+                if dh is not None and clauset_out is not None:
+                    c = dh[j][4 * dk : 4 * dk + 8]
+                    clausets[i] = {"alpha": float(c[0]), "xmin": float(c[1]), "ks_distance": float(c[2]),
+                                   "xmin_index": int(c[3]), "tail_count": int(c[4])}
                 r = rec[j]
                 records[i] = r
                 records[i]["item"] = i
@@ -361,6 +373,8 @@ class SpectraEngine:
                     svs[i] = sv[res.sv_offsets[j] : res.sv_offsets[j + 1]].copy()
         if dist_out is not None:
             dist_out[:] = dists
+        if clauset_out is not None:
+            clauset_out[:] = clausets
         return metrics, svs, records
 
 

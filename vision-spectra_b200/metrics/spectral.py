@@ -334,3 +334,19 @@ class SpectralTracker:
                 )
             )
         return tracker
+
+
+def clauset_power_law_fit(weight_matrix) -> dict[str, float]:
+    """Extra output (BASELINE north_star stage 3; the reference has no counterpart): Clauset-Shalizi-Newman
+    x_min scan on the eigenvalue spectrum -- MLE alpha and Kolmogorov-Smirnov distance for every candidate cutoff in
+    parallel on the device, the best cutoff returned: alpha, xmin, ks_distance, xmin_index (0 = largest eigenvalue),
+    tail_count.  NaN / -1 for non-2-D input or fewer than eight positive eigenvalues."""
+    nan = float("nan")
+    if not _is_2d(weight_matrix):
+        return {"alpha": nan, "xmin": nan, "ks_distance": nan, "xmin_index": -1, "tail_count": -1}
+    from ..engine import default_engine
+
+    dev = weight_matrix.device if getattr(getattr(weight_matrix, "device", None), "type", "") == "cuda" else None
+    out: list = []
+    default_engine(dev).analyze([weight_matrix], want_sv=False, clauset_out=out)
+    return out[0] if out[0] is not None else {"alpha": nan, "xmin": nan, "ks_distance": nan, "xmin_index": -1, "tail_count": -1}

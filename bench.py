@@ -475,14 +475,18 @@ def extra_single_checkpoint_latency(dev, reps: int = 30) -> dict:
             "matrices": len(out["per_layer_metrics"]), "ms_median": statistics.median(times), "ms_min": min(times), "reps": reps}
 
 
-def measure_h2d_ceiling(dev, nbytes: int, sync_all, reps: int = 10) -> float:
+def measure_h2d_ceiling(dev, nbytes: int, sync_all, reps: int = 10, src=None) -> float:
     """Pinned host -> device copy bandwidth (GB/s) of this rank while EVERY rank copies at the same time: the ceiling
-    of the e2e arm's input path on this host (its copies have the same size)."""
+    of the e2e arm's input path on this host (its copies have the same size; `src` = the very pinned block the e2e
+    arm copies from, so allocation type and placement are the same)."""
     import torch
     import torch.distributed as dist
 
-    h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
-    h.fill_(1)  # touch every page before timing
+    if src is not None:
+        h = src.view(torch.uint8)[:nbytes]
+    else:
+        h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        h.fill_(1)  # touch every page before timing
     d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     for _ in range(3):
         d.copy_(h, non_blocking=True)
@@ -647,7 +651,7 @@ def run_b200_arm(args) -> None:
     # H2D ceiling of this host at this rank count (all ranks copy at once; same copy size as the e2e chunks)
     e2e_step_s = float(e2e_s.item()) / e2e_steps
     h2d_achieved = in_bytes / 1e9 / e2e_step_s
-    h2d_ceiling = measure_h2d_ceiling(dev, min(in_bytes, args.chunk * lay.bytes), sync_all)
+    h2d_ceiling = measure_h2d_ceiling(dev, min(in_bytes, args.chunk * lay.bytes), sync_all, src=host_block)
 
     # ---------------- sampled parity check of the last e2e step against the oracle (rank 0, outside the timed regions)
     parity = None

@@ -161,8 +161,9 @@ class SweepRunner:
                  rotating compute lanes; records and singular values come back per chunk.
     """
 
-    def __init__(self, engine: SpectraEngine, layout: CheckpointLayout, ckpts_per_chunk: int = 8, lanes: int = 6):
+    def __init__(self, engine: SpectraEngine, layout: CheckpointLayout, ckpts_per_chunk: int = 8, lanes: int = 6, ramp: bool = True):
         self.engine = engine
+        self.ramp = ramp
         self.layout = layout
         self.chunk = max(1, ckpts_per_chunk)
         self.nlanes = max(1, lanes)
@@ -247,6 +248,25 @@ class SweepRunner:
         np.cumsum(np.minimum(rows_all, cols_all), out=offs[1:])
         return BatchResult(records, sv, offs, nck * mats)
 
+    def _chunk_starts(self, nck: int) -> list[int]:
+        """Chunk boundaries of run_host: ramp up 1/4, 1/2 of a chunk, full chunks, ramp down 1/2, 1/4."""
+        c = self.chunk
+        if not self.ramp or nck < 4 * c or c < 4:
+            return list(range(0, nck, c)) + [nck]
+        head, tail = [c // 4, c // 2], [c // 2, c // 4]
+        mid = nck - sum(head) - sum(tail)
+        full, rem = divmod(mid, c)
+        body = [c] * full
+        if rem and full:  # no tiny remainder chunk: split (chunk + remainder) evenly instead
+            body[-1:] = [(c + rem + 1) // 2, (c + rem) // 2]
+        elif rem:
+            body = [rem]
+        sizes = head + body + tail
+        starts = [0]
+        for sz in sizes:
+            starts.append(starts[-1] + sz)
+        return starts
+
     def run_host(self, arenas: list[torch.Tensor], want_sv: bool = True) -> tuple[np.ndarray, np.ndarray | None]:
         eng, lay = self.engine, self.layout
         dev = eng.device
@@ -267,8 +287,11 @@ class SweepRunner:
         L = self.nlanes
         free = [None] * L  # event: slot's previous consumer finished
         keep = []
-        for ci, c0 in enumerate(range(0, nck, self.chunk)):
-            chunk = arenas[c0 : c0 + self.chunk]
+        # chunk schedule: short chunks at both ends (the first chunk's copy and the last chunk's kernels are the only
+        # parts of the step that do not overlap anything), full ones in between
+        starts = self._chunk_starts(nck)
+        for ci, (c0, c1) in enumerate(zip(starts[:-1], starts[1:])):
+            chunk = arenas[c0:c1]
             slot = self._slots[ci % L]
             lane_eng, lane_stream = self._lanes[ci % L]
             with torch.cuda.stream(copy):
@@ -312,7 +335,6 @@ class SweepRunner:
             main.wait_stream(cs)
         main.synchronize()
         rec = rec_host.numpy().view(nat.RECORD_DTYPE).copy()
-        for ci, c0 in enumerate(range(0, nck, self.chunk)):  # records carry chunk-local item ids
-            cnt = min(self.chunk, nck - c0) * mats
-            rec["item"][c0 * mats : c0 * mats + cnt] += c0 * mats
+        for c0, c1 in zip(starts[:-1], starts[1:]):  # records carry chunk-local item ids
+            rec["item"][c0 * mats : c1 * mats] += c0 * mats
         return rec, (sv_host.numpy().copy() if want_sv else None)

@@ -16,6 +16,7 @@ from .spectral import (
     SpectralTracker,
     aggregate_spectral_metrics,
     alpha_exponent,
+    clauset_power_law_fit,
     get_spectral_distribution,
     get_spectral_metrics,
     power_law_alpha_hill,
@@ -42,4 +43,5 @@ __all__ = [
     "WeightInfo",
     "group_weights_by_layer",
     "group_weights_by_type",
+    "clauset_power_law_fit",  # extra: no counterpart in the reference
 ]

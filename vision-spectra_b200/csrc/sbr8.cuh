@@ -52,9 +52,12 @@ VSP_HD int64_t sbr8_band_doubles(int n) { return (int64_t)kBandW * sbr8_order(n)
 VSP_HD int sbr8_band_off(int n) { return tile_off(sbr8_order(n) >> 3, 0); }  // doubles: behind the tiled triangle
 // shared memory (doubles): V W U [8][st] | T 64 | Zpart [NW][64] | S scratch [NW][64] | tiles
 __host__ __device__ inline size_t sbr8_fixed_doubles(int st, int nw) { return (size_t)24 * st + 64 + (size_t)128 * nw; }
+__host__ __device__ inline size_t sbr8_smem_bytes_tiles(int tiles, int st, int nw) {
+    return sizeof(double) * (sbr8_fixed_doubles(st, nw) + (size_t)tiles * 64);
+}
 __host__ __device__ inline size_t sbr8_smem_bytes(int N_active, int st, int nw) {
     const int nt = N_active >> 3;
-    return sizeof(double) * (sbr8_fixed_doubles(st, nw) + (size_t)tile_off(nt, 0));
+    return sbr8_smem_bytes_tiles((nt * (nt + 1)) >> 1, st, nw);
 }
 
 #if defined(__CUDACC__)
@@ -62,6 +65,28 @@ __host__ __device__ inline size_t sbr8_smem_bytes(int N_active, int st, int nw) 
 __device__ __forceinline__ void dmma8(double& d0, double& d1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
+
+// Where the tiles live: the first ts64 / 64 tiles (the top tile rows: they survive longest) in shared memory, the rest
+// in place in the item's global workspace region (L2).  All-shared launches pass ts64 >= the triangle's size and never
+// take the global branch; the first order range of n > 136 runs two CTAs per SM with its bottom tile rows in L2 --
+// they are eliminated first, so the global share shrinks to nothing by the time the range hands over.  A tile is 512
+// contiguous bytes: one fully coalesced 128-bit access per lane either way.  `off` is warp-uniform.
+template <bool L2>  // false: every tile in shared memory (no branch, no extra registers in the capped instantiations)
+struct TileMem {
+    double* A;
+    double* G;
+    int ts64;
+    __device__ __forceinline__ double2 load(int off, int lane) const {
+        if (!L2) return *(reinterpret_cast<const double2*>(A + off) + lane);
+        return off < ts64 ? *(reinterpret_cast<const double2*>(A + off) + lane) : __ldcg(reinterpret_cast<const double2*>(G + off) + lane);
+    }
+    __device__ __forceinline__ void store(int off, int lane, double2 v) const {
+        if (!L2 || off < ts64)
+            *(reinterpret_cast<double2*>(A + off) + lane) = v;
+        else
+            *(reinterpret_cast<double2*>(G + off) + lane) = v;
+    }
+};
 
 // A -= V W^T + W V^T on one tile (rows 8I.., columns 8J..): operands as fragments
 //   a*: -V / -W [k = 4 s + t][row g]      b*: W / V [k = 4 s + t][col g]
@@ -84,27 +109,75 @@ __device__ __forceinline__ void sbr8_tile_update(double2& c, const Frag8& ra, co
     dmma8(c.x, c.y, -ra.w1, cb.v1);
 }
 
-// pending update of the leading nt x nt tile triangle; worker w of nwk takes tiles w, w + nwk, ... (linear order)
-__device__ __forceinline__ void sbr8_update_sweep(double* __restrict__ A, int nt, int worker, int nwk, const double* Vb,
-                                                  const double* Wb, int st, int lane, int g, int t) {
-    const int total = (nt * (nt + 1)) >> 1;
-    int I = 0, J = worker;
-    while (J > I) {
-        J -= I + 1;
-        ++I;
-    }
-    for (int tau = worker; tau < total; tau += nwk) {
-        double2* tp = reinterpret_cast<double2*>(A + tile_off(I, J)) + lane;
-        double2 c = *tp;
-        const Frag8 ra = sbr8_frag(Vb, Wb, st, 8 * I, g, t);
-        const Frag8 cb = sbr8_frag(Vb, Wb, st, 8 * J, g, t);
-        sbr8_tile_update(c, ra, cb);
-        *tp = c;
-        J += nwk;
+// pending update of the leading nt x nt tile triangle; worker w of nwk takes tiles w, w + nwk, ... (linear order), TWO
+// at a time: the four dependent DMMAs of a tile are a 104-cycle chain, a second tile's chain fills the pipe meanwhile;
+// the next pair is fetched while the current one is in the pipe (it may come from L2)
+struct TilePos {
+    int I, J;
+    __device__ __forceinline__ void advance(int by) {
+        J += by;
         while (J > I) {
             J -= I + 1;
             ++I;
         }
+    }
+};
+template <bool PAIR>
+__device__ __forceinline__ void sbr8_update_sweep(const TileMem<PAIR>& tm, int nt, int worker, int nwk, const double* Vb,
+                                                  const double* Wb, int st, int lane, int g, int t) {
+    const int total = (nt * (nt + 1)) >> 1;
+    if (worker >= total) return;
+    if (!PAIR) {  // one tile at a time, all in shared memory (the register-capped instantiations)
+        TilePos p{0, 0};
+        p.advance(worker);
+        for (int tau = worker; tau < total; tau += nwk) {
+            double2 c = tm.load(tile_off(p.I, p.J), lane);
+            const Frag8 ra = sbr8_frag(Vb, Wb, st, 8 * p.I, g, t);
+            const Frag8 cb = sbr8_frag(Vb, Wb, st, 8 * p.J, g, t);
+            sbr8_tile_update(c, ra, cb);
+            tm.store(tile_off(p.I, p.J), lane, c);
+            p.advance(nwk);
+        }
+        return;
+    }
+    TilePos p0{0, 0}, p1;
+    p0.advance(worker);
+    p1 = p0;
+    p1.advance(nwk);
+    bool two = worker + nwk < total;
+    double2 c0 = tm.load(tile_off(p0.I, p0.J), lane);
+    double2 c1 = two ? tm.load(tile_off(p1.I, p1.J), lane) : make_double2(0.0, 0.0);
+    for (int tau = worker; tau < total; tau += 2 * nwk) {
+        TilePos q0 = p1, q1;
+        q0.advance(nwk);
+        q1 = q0;
+        q1.advance(nwk);
+        const bool n0 = tau + 2 * nwk < total, n1 = tau + 3 * nwk < total;
+        double2 d0 = make_double2(0.0, 0.0), d1 = make_double2(0.0, 0.0);
+        if (n0) d0 = tm.load(tile_off(q0.I, q0.J), lane);
+        if (n1) d1 = tm.load(tile_off(q1.I, q1.J), lane);
+        const Frag8 ra0 = sbr8_frag(Vb, Wb, st, 8 * p0.I, g, t), cb0 = sbr8_frag(Vb, Wb, st, 8 * p0.J, g, t);
+        if (two) {
+            const Frag8 ra1 = sbr8_frag(Vb, Wb, st, 8 * p1.I, g, t), cb1 = sbr8_frag(Vb, Wb, st, 8 * p1.J, g, t);
+            dmma8(c0.x, c0.y, -ra0.v0, cb0.w0);
+            dmma8(c1.x, c1.y, -ra1.v0, cb1.w0);
+            dmma8(c0.x, c0.y, -ra0.v1, cb0.w1);
+            dmma8(c1.x, c1.y, -ra1.v1, cb1.w1);
+            dmma8(c0.x, c0.y, -ra0.w0, cb0.v0);
+            dmma8(c1.x, c1.y, -ra1.w0, cb1.v0);
+            dmma8(c0.x, c0.y, -ra0.w1, cb0.v1);
+            dmma8(c1.x, c1.y, -ra1.w1, cb1.v1);
+            tm.store(tile_off(p0.I, p0.J), lane, c0);
+            tm.store(tile_off(p1.I, p1.J), lane, c1);
+        } else {
+            sbr8_tile_update(c0, ra0, cb0);
+            tm.store(tile_off(p0.I, p0.J), lane, c0);
+        }
+        c0 = d0;
+        c1 = d1;
+        p0 = q0;
+        p1 = q1;
+        two = n1;
     }
 }
 
@@ -224,7 +297,7 @@ __device__ __forceinline__ void sbr8_panel_lq(double* __restrict__ Ub, double* _
 //   columns: D[col g][kk] += sum_rows tile[row][g] U[kk][row]   transposed fragments by four shuffles
 // Diagonal tiles are stored full: row sums only.  Tile rows >= nt do not exist.
 template <int TB>
-__device__ __forceinline__ void sbr8_symm_block(const double* __restrict__ A, bool diag, int RT0, int CT0, int tr0, int tre,
+__device__ __forceinline__ void sbr8_symm_block(const TileMem<TB == 4>& tm, bool diag, int RT0, int CT0, int tr0, int tre,
                                                 int nt, const double* __restrict__ Ub, int st, int lane, int g, int t,
                                                 double (&rowsum)[TB][2], double (&colsum)[TB][2]) {
     double2 c[TB][TB];
@@ -233,7 +306,7 @@ __device__ __forceinline__ void sbr8_symm_block(const double* __restrict__ A, bo
 #pragma unroll
         for (int tc = 0; tc < TB; ++tc) {
             const bool ok = tr >= tr0 && tr < tre && RT0 + tr < nt && !(diag && tc > tr);
-            c[tr][tc] = ok ? *(reinterpret_cast<const double2*>(A + tile_off(RT0 + tr, CT0 + tc)) + lane) : make_double2(0.0, 0.0);
+            c[tr][tc] = ok ? tm.load(tile_off(RT0 + tr, CT0 + tc), lane) : make_double2(0.0, 0.0);
         }
     double2 bu[TB];  // U[kk = g][cols 2t, 2t+1 of tile column tc]
 #pragma unroll
@@ -272,7 +345,8 @@ __device__ __forceinline__ void sbr8_symm_block(const double* __restrict__ A, bo
 // index-block side of the cyclic products schedule (2: blocks of 16, 4: blocks of 32): NW * 8 TB >= m_start - 8.
 template <int NW, int MINB, int NC, int TB>
 __global__ void __launch_bounds__(32 * NW, MINB)
-    sbr8_kernel(const ItemDesc* __restrict__ items, int item_base, double* __restrict__ ws, int st, int m_start, int m_stop) {
+    sbr8_kernel(const ItemDesc* __restrict__ items, int item_base, double* __restrict__ ws, int st, int m_start, int m_stop,
+                int tiles_smem) {
     extern __shared__ __align__(16) double smem[];
     const ItemDesc it = items[item_base + blockIdx.x];
     const int n = it.n;
@@ -281,6 +355,7 @@ __global__ void __launch_bounds__(32 * NW, MINB)
     constexpr int nthreads = 32 * NW;
     const int lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int g = lane >> 2, t = lane & 3;  // DMMA fragment coordinates
+    constexpr bool kPair = (TB == 4);       // the two-CTA-per-SM instantiation (168 registers): two tiles in flight
 
     double* Vb = smem;              // [8][st] previous reflectors (pending update); partner sums during the products
     double* Wb = Vb + 8 * st;       // [8][st] previous W; partner sums / Y / X / new W
@@ -295,10 +370,12 @@ __global__ void __launch_bounds__(32 * NW, MINB)
     double* __restrict__ Bd = G + sbr8_band_off(n);  // band output, frame indices
     const int n0 = m_start > 0 ? m_start : N;            // order this launch starts from
     const int nt0 = n0 >> 3;
+    const int tot64 = tile_off(nt0, 0);                  // doubles of this launch's triangle
+    const int ts64 = (tiles_smem << 6) < tot64 ? (tiles_smem << 6) : tot64;  // ... of which in shared memory
+    const TileMem<TB == 4> tm{A, G, ts64};
     if (m_start > 0) {
         if (out[2 * n + MISC_FLAGS] != 0.0) return;  // non-finite / all-zero: flagged by the first launch
-        const int cnt = tile_off(nt0, 0);
-        for (int i = tid; i < cnt; i += nthreads) A[i] = G[i];  // handed over in tile order
+        for (int i = tid; i < ts64; i += nthreads) A[i] = G[i];  // handed over in tile order
     } else {
         // ---- condition the Gram matrix (power-of-four scale so that |G_ij| <= 1 and the singular values un-scale
         //      exactly; NaN/Inf anywhere in W shows on the Gram diagonal).  The Gram kernels wrote the tile layout.
@@ -341,14 +418,16 @@ __global__ void __launch_bounds__(32 * NW, MINB)
             out[2 * n + MISC_FLAGS] = 0.0;
             out[2 * n + MISC_SLOT] = -1.0;
         }
-        const int cnt2 = tile_off(nt0, 0) >> 1;  // flat, coalesced 128-bit copy
-        const double2* __restrict__ G2 = reinterpret_cast<const double2*>(G);
+        double2* G2 = reinterpret_cast<double2*>(G);  // flat, coalesced 128-bit copy; the global share is scaled in place
         double2* A2 = reinterpret_cast<double2*>(A);
-        for (int i = tid; i < cnt2; i += nthreads) {
+        for (int i = tid; i < (tot64 >> 1); i += nthreads) {
             double2 v = G2[i];
             v.x *= scale;
             v.y *= scale;
-            A2[i] = v;
+            if (2 * i < ts64)
+                A2[i] = v;
+            else
+                G2[i] = v;
         }
     }
     __syncthreads();
@@ -370,19 +449,35 @@ __global__ void __launch_bounds__(32 * NW, MINB)
     while (m >= 16 && m > m_stop) {
         const int p0 = m - 8, Ip = p0 >> 3;
         // ---- (1) mini-pass: tile row Ip with the pending update; diagonal tile -> band, the rest -> panel buffer
-        for (int J = warp; J <= Ip; J += NW) {
-            double2 c = *(reinterpret_cast<const double2*>(A + tile_off(Ip, J)) + lane);
-            if (pending) {
-                const Frag8 ra = sbr8_frag(Vb, Wb, st, p0, g, t);
-                const Frag8 cb = sbr8_frag(Vb, Wb, st, 8 * J, g, t);
-                sbr8_tile_update(c, ra, cb);
+        {
+            // a warp's tiles J = warp, warp + NW, ... (at most kMini of them): all loads first (they may come from L2)
+            constexpr int kMini = kPair ? (kSbr8MaxN / 8 + NW - 1) / NW : 1;  // (register-capped instantiations: one at a time)
+            Frag8 ra;
+            if (pending) ra = sbr8_frag(Vb, Wb, st, p0, g, t);
+            for (int Jb = warp; Jb <= Ip; Jb += kMini * NW) {
+            double2 cm[kMini];
+#pragma unroll
+            for (int q = 0; q < kMini; ++q) {
+                const int J = Jb + q * NW;
+                cm[q] = (J <= Ip) ? tm.load(tile_off(Ip, J), lane) : make_double2(0.0, 0.0);
             }
-            if (J < Ip) {
-                *reinterpret_cast<double2*>(Ub + (7 - g) * st + 8 * J + 2 * t) = c;
-            } else {
-                double* brow = Bd + (p0 + g) * kBandW + g;
-                if (2 * t <= g) brow[-2 * t] = c.x;
-                if (2 * t + 1 <= g) brow[-2 * t - 1] = c.y;
+#pragma unroll
+            for (int q = 0; q < kMini; ++q) {
+                const int J = Jb + q * NW;
+                if (J > Ip) continue;  // warp-uniform
+                double2 c = cm[q];
+                if (pending) {
+                    const Frag8 cb = sbr8_frag(Vb, Wb, st, 8 * J, g, t);
+                    sbr8_tile_update(c, ra, cb);
+                }
+                if (J < Ip) {
+                    *reinterpret_cast<double2*>(Ub + (7 - g) * st + 8 * J + 2 * t) = c;
+                } else {
+                    double* brow = Bd + (p0 + g) * kBandW + g;
+                    if (2 * t <= g) brow[-2 * t] = c.x;
+                    if (2 * t + 1 <= g) brow[-2 * t - 1] = c.y;
+                }
+            }
             }
         }
         __syncthreads();
@@ -396,12 +491,12 @@ __global__ void __launch_bounds__(32 * NW, MINB)
         // (measured: LQ 10.4 k cycles per panel with eleven update warps).
         if (warp == NW - 1) {
             sbr8_panel_lq<NC>(Ub, Tm, Bd, p0, st, lane);
-            if (NW == 1 && pending) sbr8_update_sweep(A, Ip, 0, 1, Vb, Wb, st, lane, g, t);
+            if (NW == 1 && pending) sbr8_update_sweep<kPair>(tm, Ip, 0, 1, Vb, Wb, st, lane, g, t);
         } else if (pending) {
             if (kQuietLq && NW >= 8) {
-                if ((warp & 3) != 3) sbr8_update_sweep(A, Ip, warp - (warp >> 2), NW - NW / 4, Vb, Wb, st, lane, g, t);
+                if ((warp & 3) != 3) sbr8_update_sweep<kPair>(tm, Ip, warp - (warp >> 2), NW - NW / 4, Vb, Wb, st, lane, g, t);
             } else {
-                sbr8_update_sweep(A, Ip, warp, NW - 1, Vb, Wb, st, lane, g, t);
+                sbr8_update_sweep<kPair>(tm, Ip, warp, NW - 1, Vb, Wb, st, lane, g, t);
             }
         }
         VSP_LAP(1);
@@ -432,9 +527,9 @@ __global__ void __launch_bounds__(32 * NW, MINB)
 #pragma unroll
                     for (int i = 0; i < TB; ++i) oth[i][0] = oth[i][1] = 0.0;
                     if (own_cols)
-                        sbr8_symm_block<TB>(A, s == 0, TB * rb, TB * cb, tr0, tre, Ip, Ub, st, lane, g, t, oth, own);
+                        sbr8_symm_block<TB>(tm, s == 0, TB * rb, TB * cb, tr0, tre, Ip, Ub, st, lane, g, t, oth, own);
                     else
-                        sbr8_symm_block<TB>(A, s == 0, TB * rb, TB * cb, tr0, tre, Ip, Ub, st, lane, g, t, own, oth);
+                        sbr8_symm_block<TB>(tm, s == 0, TB * rb, TB * cb, tr0, tre, Ip, Ub, st, lane, g, t, own, oth);
                     double* const yb = Ybuf[s & 1];
 #pragma unroll
                     for (int i = 0; i < TB; ++i) {
@@ -549,9 +644,9 @@ __global__ void __launch_bounds__(32 * NW, MINB)
     const int ntm = m >> 3;
     if (m >= 16) {
         // ---- hand-over: bring the leading m x m block up to date and return it to the workspace in tile order
-        if (pending) sbr8_update_sweep(A, ntm, warp, NW, Vb, Wb, st, lane, g, t);
+        if (pending) sbr8_update_sweep<kPair>(tm, ntm, warp, NW, Vb, Wb, st, lane, g, t);
         __syncthreads();
-        const int cnt = tile_off(ntm, 0);
+        const int cnt = tile_off(ntm, 0) < ts64 ? tile_off(ntm, 0) : ts64;  // the global share is already in place
         for (int i = tid; i < cnt; i += nthreads) G[i] = A[i];
         return;
     }

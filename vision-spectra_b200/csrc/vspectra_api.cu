@@ -526,18 +526,26 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
                 int m_stop = order > 136 ? 128 : (order > 72 ? 64 : 0);
                 static const bool one_launch8 = std::getenv("VSP_SBR8_ONE_LAUNCH") != nullptr;  // experiments
                 if (one_launch8) m_stop = 0;
-#define VSP_SBR8_LAUNCH(NW, MINB, NC, TB)                                                                               \
+#define VSP_SBR8_LAUNCH(NW, MINB, NC, TB, TILES)                                                                        \
     {                                                                                                                   \
-        const size_t smem = sbr8_smem_bytes(order, stv, NW);                                                            \
+        const int all_tiles = ((order >> 3) * ((order >> 3) + 1)) >> 1;                                                 \
+        const int tiles = std::min(all_tiles, (int)(TILES));                                                            \
+        const size_t smem = sbr8_smem_bytes_tiles(tiles, stv, NW);                                                      \
         VSP_CUDA(cudaFuncSetAttribute(sbr8_kernel<NW, MINB, NC, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                       (int)std::max<size_t>(smem, 48 * 1024)));                                         \
         VSP_CUDA(cudaFuncSetAttribute(sbr8_kernel<NW, MINB, NC, TB>, cudaFuncAttributePreferredSharedMemoryCarveout,    \
                                       cudaSharedmemCarveoutMaxShared));                                                 \
-        sbr8_kernel<NW, MINB, NC, TB><<<c.count, 32 * NW, smem, st>>>(p->d_items, c.begin, ws, stv, m_start, m_stop);   \
+        sbr8_kernel<NW, MINB, NC, TB><<<c.count, 32 * NW, smem, st>>>(p->d_items, c.begin, ws, stv, m_start, m_stop,    \
+                                                                       tiles);                                          \
     }
-                if (order > 136) VSP_SBR8_LAUNCH(12, 1, 6, 2)
-                else if (order > 72) VSP_SBR8_LAUNCH(8, 2, 4, 2)
-                else VSP_SBR8_LAUNCH(4, 4, 2, 2)
+                // n > 136: two CTAs per SM (six warps each) with the bottom tile rows in L2 while they last, or
+                // (VSP_SBR8_LONE=1) one twelve-warp CTA per SM with everything in shared memory
+                static const bool lone = std::getenv("VSP_SBR8_LONE") != nullptr;
+                const int two_tiles = (int)((112 * 1024 - sizeof(double) * sbr8_fixed_doubles(stv, 6)) / 512);
+                if (order > 136 && !lone) VSP_SBR8_LAUNCH(6, 2, 6, 4, two_tiles)
+                else if (order > 136) VSP_SBR8_LAUNCH(12, 1, 6, 2, 1 << 20)
+                else if (order > 72) VSP_SBR8_LAUNCH(8, 2, 4, 2, 1 << 20)
+                else VSP_SBR8_LAUNCH(4, 4, 2, 2, 1 << 20)
 #undef VSP_SBR8_LAUNCH
                 g_launches++;
                 t_timer.tick("sbr8", st);

@@ -387,7 +387,8 @@ static int plan_layout(vsp_plan* p, int32_t count, const int32_t* rows, const in
                 static const bool old_refine = std::getenv("VSP_REFINE_OLD") != nullptr;
                 int kmax = 0;
                 int64_t min_share = INT64_MAX;
-                const int B = c.n <= 256 ? 4 : kRcMaxCluster;
+                int B = c.n <= 256 ? 4 : kRcMaxCluster;
+                if (const char* e = std::getenv("VSP_REFINE_B")) B = std::max(1, std::min(kRcMaxCluster, std::atoi(e)));  // experiments
                 for (int s = c.begin; s < c.begin + c.count; ++s) {
                     kmax = std::max(kmax, p->items[s].kdim);
                     min_share = std::min<int64_t>(min_share, (int64_t)((c.n + B - 1) / B) * p->items[s].kdim);
@@ -397,12 +398,15 @@ static int plan_layout(vsp_plan* p, int32_t count, const int32_t* rows, const in
                 // a CTA's share of X stays in shared memory when it is small (the square matrices of ViT-Tiny: 74 KB),
                 // which leaves room for bisection CTAs on the same SM; larger shares work from the L2-resident pool
                 c.refine_xs_cap = (min_share <= 12288) ? 12288 : 0;
+                if (const char* e = std::getenv("VSP_REFINE_XS")) c.refine_xs_cap = std::atoi(e);  // experiments
                 if (c.refine_B > 0)
                     c.refine_slot_doubles = round_up64(refine_cluster_slot_doubles(kmax, c.n, c.refine_B), 4);
             }
             // pool buffers = CTAs of the re-solve launch (1024 threads: one per SM); more flagged items than
             // buffers are served in rounds, so the pool never limits how many items can be re-solved
             c.refine_slots = std::min(c.count, std::max(4, std::min(c.count / 8, 2 * 148)));
+            // cluster re-solve: no more clusters than can be resident at once (each loops over the work list)
+            if (c.refine_B > 0) c.refine_slots = std::min(c.refine_slots, std::max(4, 148 / c.refine_B));
             c.refine_counter = idx++;
             c.refine_items_off = roff;  // work list: one entry per item of the class
             roff += round_up64((int64_t)c.count * 4, 1024);

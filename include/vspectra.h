@@ -191,6 +191,17 @@ int vsp_analyze_batch_host(const void* const* h_ptrs, const int32_t* rows, const
                            const vsp_opts* opts, double* h_sv, vsp_record* h_records,
                            int32_t device);
 
+/* Batched FP64 GEMM on the FP64 tensor cores, the building block of the singular-vector consumers (SURVEY 8f rank 4:
+ * metrics/tail_truncation.py:63-152, metrics/gradient_alignment.py:48-70 -- evaluated as Newton-Schulz matrix
+ * functions of W, vision_spectra_b200/lowrank.py):
+ *     C[b] = alpha * op(A[b]) * op(B[b]) + beta * C[b] + gamma * I,   op(X) = X or X^T (trans flag), row-major f64,
+ * M x N results, contraction length K.  d_A / d_B / d_C are DEVICE arrays of `batch` DEVICE pointers (batch <= 65535);
+ * C must not alias A or B.  Asynchronous on `stream`. */
+int vsp_dgemm_batched(int32_t batch, int32_t M, int32_t N, int32_t K, double alpha,
+                      const double* const* d_A, int64_t lda, int32_t transA,
+                      const double* const* d_B, int64_t ldb, int32_t transB,
+                      double beta, double gamma, double* const* d_C, int64_t ldc, void* stream);
+
 /* Counters for bench.py's `gpu_launches`: kernels launched by this library in this
  * process since load (or since the last reset). */
 int64_t vsp_kernel_launch_count(void);

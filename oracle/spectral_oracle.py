@@ -495,3 +495,41 @@ def clauset_xmin_scan(w):
         return out
     D, a, k = best
     return {"alpha": a, "xmin": float(lam[k]), "ks_distance": D, "xmin_index": m - 1 - k, "tail_count": m - k}
+
+
+# -------------------------------------------------------------------- singular-vector consumers (8f rank 4)
+def truncate_weight_matrix(weight, retention_ratio=0.9, min_rank=1):
+    """metrics/tail_truncation.py:63-105, restated (full SVD with vectors, SciPy)."""
+    from scipy.linalg import svd
+
+    U, s, Vt = svd(np.asarray(weight).astype(np.float64), full_matrices=False)
+    k = min(max(min_rank, int(np.ceil(len(s) * retention_ratio))), len(s))
+    st = s.copy()
+    st[k:] = 0.0
+    total = np.sum(s**2)
+    return (U @ np.diag(st) @ Vt).astype(np.asarray(weight).dtype), {
+        "original_rank": int(np.sum(s > 1e-10)), "truncated_rank": k, "energy_retained": float(np.sum(st**2) / total) if total > 0 else 1.0}
+
+
+def truncate_by_energy(weight, energy_threshold=0.99, min_rank=1):
+    """metrics/tail_truncation.py:108-152, restated."""
+    from scipy.linalg import svd
+
+    U, s, Vt = svd(np.asarray(weight).astype(np.float64), full_matrices=False)
+    total = np.sum(s**2)
+    if total <= 0:
+        return weight, {"original_rank": 0, "truncated_rank": 0, "energy_retained": 1.0}
+    k = int(np.searchsorted(np.cumsum(s**2) / total, energy_threshold) + 1)
+    k = max(min_rank, min(k, len(s)))
+    st = s.copy()
+    st[k:] = 0.0
+    return (U @ np.diag(st) @ Vt).astype(np.asarray(weight).dtype), {
+        "original_rank": int(np.sum(s > 1e-10)), "truncated_rank": int(k), "energy_retained": float(np.sum(st**2) / total)}
+
+
+def compute_rank_reducing_gradient(weight):
+    """metrics/gradient_alignment.py:48-70, restated: U @ Vt."""
+    from scipy.linalg import svd
+
+    U, s, Vt = svd(np.asarray(weight).astype(np.float64), full_matrices=False)
+    return U @ Vt

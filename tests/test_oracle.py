@@ -126,3 +126,29 @@ def test_distribution_invariants():  # :321-345
     d = orc.get_spectral_distribution(np.random.randn(64, 64), name="t", matrix_type="x")
     assert np.all(np.diff(d.singular_values) <= 0) and np.all(d.normalized_sv <= 1.0)
     assert np.all(np.diff(d.cumulative_variance) >= 0) and np.isclose(d.cumulative_variance[-1], 1.0)
+
+
+def test_lowrank_restatements_match_the_reference_goldens():
+    """oracle restatements of tail_truncation.py:63-152 and gradient_alignment.py:48-70 against outputs of the real
+    reference (tests/golden/lowrank_golden.npz, oracle/gen_golden_lowrank.py)."""
+    from pathlib import Path
+
+    from _inputs import build_case
+
+    gold = np.load(Path(__file__).parent / "golden" / "lowrank_golden.npz")
+    names = sorted({k.split("/")[0] for k in gold.files})
+    assert len(names) == 6
+    for key in names:
+        case = {"vit_C_0_q": "vit:C:0:q", "vit_C_0_mlp_up": "vit:C:0:mlp_up", "vit_E_0_mlp_down": "vit:E:0:mlp_down",
+                "randn_30x50_f64": "randn:30x50:f64", "sgd_96x384": "sgd:96x384", "powerlaw_64_0.5_f32": "powerlaw:64:0.5:f32"}[key]
+        w = build_case(case)
+        t90, i90 = orc.truncate_weight_matrix(w, 0.9)
+        t50, i50 = orc.truncate_weight_matrix(w, 0.5)
+        te, ie = orc.truncate_by_energy(w, 0.95)
+        np.testing.assert_allclose(t90, gold[f"{key}/trunc90"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(t50, gold[f"{key}/trunc50"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(te, gold[f"{key}/energy95"], rtol=0, atol=1e-12)
+        info = gold[f"{key}/info"]
+        assert (i90["original_rank"], i90["truncated_rank"], i50["truncated_rank"], ie["truncated_rank"]) == tuple(int(v) for v in info[[0, 1, 3, 5]])
+        np.testing.assert_allclose([i90["energy_retained"], i50["energy_retained"], ie["energy_retained"]], info[[2, 4, 6]], rtol=1e-12)
+        np.testing.assert_allclose(orc.compute_rank_reducing_gradient(w), gold[f"{key}/polar"], rtol=0, atol=1e-10)

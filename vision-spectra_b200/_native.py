@@ -131,6 +131,11 @@ def load() -> ctypes.CDLL:
             c_int32,
             [POINTER(c_void_p), P32, P32, P64, c_int32, c_int32, POINTER(VspOpts), POINTER(c_double), c_void_p, c_int32],
         ),
+        "vsp_dgemm_batched": (
+            c_int32,
+            [c_int32, c_int32, c_int32, c_int32, c_double, c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_double, c_double,
+             c_void_p, c_int64, c_void_p],
+        ),
         "vsp_kernel_launch_count": (c_int64, []),
         "vsp_reset_kernel_launch_count": (None, []),
     }
@@ -154,6 +159,7 @@ EXPORTED_SYMBOLS = (
     "vsp_plan_destroy",
     "vsp_plan_execute",
     "vsp_plan_execute_dist",
+    "vsp_dgemm_batched",
     "vsp_plan_execute_profiled",
     "vsp_plan_debug_gram",
     "vsp_analyze_batch",

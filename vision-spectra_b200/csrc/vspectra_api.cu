@@ -20,6 +20,7 @@
 #include "eig_kernels.cuh"
 #include "gram_f64.cuh"
 #include "gram_i8.cuh"
+#include "dgemm_dmma.cuh"
 
 using namespace vsp;
 
@@ -797,6 +798,19 @@ int vsp_plan_execute_profiled(vsp_plan* p, const void* const* d_ptrs, double* d_
     }
     for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
     return rc;
+}
+
+int vsp_dgemm_batched(int32_t batch, int32_t M, int32_t N, int32_t K, double alpha, const double* const* d_A, int64_t lda,
+                      int32_t transA, const double* const* d_B, int64_t ldb, int32_t transB, double beta, double gamma,
+                      double* const* d_C, int64_t ldc, void* stream) {
+    if (batch < 0 || M < 1 || N < 1 || K < 1 || !d_A || !d_B || !d_C) return VSP_E_ARG;
+    if (batch == 0) return VSP_OK;
+    if (batch > 65535) return VSP_E_UNSUPPORTED;
+    const dim3 grid((N + kGemmTile - 1) / kGemmTile, (M + kGemmTile - 1) / kGemmTile, batch);
+    dgemm_dmma_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(M, N, K, alpha, d_A, lda, transA, d_B, ldb, transB,
+                                                                                beta, gamma, d_C, ldc);
+    g_launches++;
+    return cuda_ok(cudaGetLastError(), "dgemm_dmma_kernel") ? VSP_OK : VSP_E_CUDA;
 }
 
 int vsp_analyze_batch(const void* const* d_ptrs, const int32_t* rows, const int32_t* cols, const int64_t* ld,

@@ -44,13 +44,10 @@ __host__ __device__ inline size_t refine_cluster_tail_doubles(int npad) { return
 
 #if defined(__CUDACC__)
 
-// (124 registers x 512 threads: a re-solve CTA takes an SM's whole register file, so the bisection kernel only overlaps
-//  on the SMs without one; capping it at 64 registers was measured slower in total: 1.50 -> 1.70 ms with spills)
 template <typename TIn>
-__global__ void __launch_bounds__(kRcThreads)
-    refine_cluster_kernel(const ItemDesc* __restrict__ items, RefineGate gate, RefinePool pool, int npad, int Kpad, int nloc_max,
-                          int xs_cap, vsp_opts opts, double* __restrict__ sv_out, vsp_record* __restrict__ records,
-                          double* __restrict__ dist_out) {
+__device__ __forceinline__ void refine_cluster_body(const ItemDesc* __restrict__ items, RefineGate gate, RefinePool pool, int npad,
+                                                    int Kpad, int nloc_max, int xs_cap, vsp_opts opts, double* __restrict__ sv_out,
+                                                    vsp_record* __restrict__ records, double* __restrict__ dist_out) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) double smem[];
@@ -283,6 +280,29 @@ __global__ void __launch_bounds__(kRcThreads)
         }
         cluster.sync();  // rank 0's shared arrays are rewritten by the next entry's fill
     }
+}
+
+// Two entry points around the same body:
+//   refine_cluster_kernel        n > 256: the re-solve is the long pole (29 ms per ViT-Base chunk against 2 ms of
+//                                bisection), all registers, default carve-out (the L2-resident shares like the L1);
+//   refine_cluster_shared_kernel n <= 256: runs BESIDE the bisection kernel, so it must leave room on its SMs: at most
+//                                64 registers (124 x 512 threads took an SM's whole register file) and, set by the
+//                                host, the maximum shared-memory carve-out (with the default split no bisection CTA
+//                                fitted next to the 120 KB of a re-solve CTA).  Both were needed: stage 3 of the
+//                                Scenario-A sweep 2.65 -> 2.22 ms although the re-solve itself slows from 1.5 to 2.1 ms.
+template <typename TIn>
+__global__ void __launch_bounds__(kRcThreads)
+    refine_cluster_kernel(const ItemDesc* __restrict__ items, RefineGate gate, RefinePool pool, int npad, int Kpad, int nloc_max,
+                          int xs_cap, vsp_opts opts, double* __restrict__ sv_out, vsp_record* __restrict__ records,
+                          double* __restrict__ dist_out) {
+    refine_cluster_body<TIn>(items, gate, pool, npad, Kpad, nloc_max, xs_cap, opts, sv_out, records, dist_out);
+}
+template <typename TIn>
+__global__ void __maxnreg__(64)
+    refine_cluster_shared_kernel(const ItemDesc* __restrict__ items, RefineGate gate, RefinePool pool, int npad, int Kpad,
+                                 int nloc_max, int xs_cap, vsp_opts opts, double* __restrict__ sv_out,
+                                 vsp_record* __restrict__ records, double* __restrict__ dist_out) {
+    refine_cluster_body<TIn>(items, gate, pool, npad, Kpad, nloc_max, xs_cap, opts, sv_out, records, dist_out);
 }
 
 #endif  // __CUDACC__

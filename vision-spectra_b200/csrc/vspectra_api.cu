@@ -495,6 +495,7 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
     // per-device attribute; cheap enough to set on every call (one process may drive several GPUs)
     VSP_CUDA(cudaFuncSetAttribute(tridiag_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VSP_CUDA(cudaFuncSetAttribute(bisect_metrics_kernel<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VSP_CUDA(cudaFuncSetAttribute(bisect_metrics_kernel<128, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     VSP_CUDA(cudaFuncSetAttribute(bisect_metrics_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 
     auto mark = [&]() -> int {
@@ -670,15 +671,23 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
                 attr[0].val.clusterDim.z = 1;
                 cfg.attrs = attr;
                 cfg.numAttrs = 1;
+                const bool shared = c.n <= 256;  // runs beside the bisection kernel: capped registers, maximum carve-out
+#define VSP_RC_LAUNCH(KERNEL)                                                                                             \
+    {                                                                                                                   \
+        VSP_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(csmem, 48 * 1024))); \
+        if (shared)                                                                                                     \
+            VSP_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+        VSP_CUDA(cudaLaunchKernelEx(&cfg, KERNEL, (const ItemDesc*)p->d_items, gate, pool, c.npad, Kpad, nloc, c.refine_xs_cap, \
+                                    p->opts, d_sv, d_records, d_dist));                                                 \
+    }
                 if (p->dtype == VSP_F32) {
-                    VSP_CUDA(cudaFuncSetAttribute(refine_cluster_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(csmem, 48 * 1024)));
-                    VSP_CUDA(cudaLaunchKernelEx(&cfg, refine_cluster_kernel<float>, (const ItemDesc*)p->d_items, gate, pool, c.npad, Kpad, nloc,
-                                                c.refine_xs_cap, p->opts, d_sv, d_records, d_dist));
+                    if (shared) VSP_RC_LAUNCH(refine_cluster_shared_kernel<float>)
+                    else VSP_RC_LAUNCH(refine_cluster_kernel<float>)
                 } else {
-                    VSP_CUDA(cudaFuncSetAttribute(refine_cluster_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(csmem, 48 * 1024)));
-                    VSP_CUDA(cudaLaunchKernelEx(&cfg, refine_cluster_kernel<double>, (const ItemDesc*)p->d_items, gate, pool, c.npad, Kpad, nloc,
-                                                c.refine_xs_cap, p->opts, d_sv, d_records, d_dist));
+                    if (shared) VSP_RC_LAUNCH(refine_cluster_shared_kernel<double>)
+                    else VSP_RC_LAUNCH(refine_cluster_kernel<double>)
                 }
+#undef VSP_RC_LAUNCH
             } else if (p->dtype == VSP_F32) {
                 VSP_CUDA(cudaFuncSetAttribute(refine_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
                 refine_kernel<float><<<c.refine_slots, 1024, rsm, st>>>(p->d_items, gate, pool, c.npad, xs_doubles, p->opts, d_sv, d_records, d_dist);

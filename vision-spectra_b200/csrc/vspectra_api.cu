@@ -388,7 +388,10 @@ static int plan_layout(vsp_plan* p, int32_t count, const int32_t* rows, const in
                 static const bool old_refine = std::getenv("VSP_REFINE_OLD") != nullptr;
                 int kmax = 0;
                 int64_t min_share = INT64_MAX;
-                int B = c.n <= 256 ? 4 : kRcMaxCluster;
+                // n <= 256: THREE CTAs per matrix.  A 192 x 192 share is then exactly the 96 KB shared-memory cap, and the
+                // co-residency limit (clusters do not span GPCs) is ~46 clusters instead of ~33: the Scenario-A sweep flags
+                // 36 matrices per step, which four-CTA clusters served in two rounds (re-solve 3.6 ms, three-CTA 2.3 ms)
+                int B = c.n <= 256 ? 3 : kRcMaxCluster;
                 if (const char* e = std::getenv("VSP_REFINE_B")) B = std::max(1, std::min(kRcMaxCluster, std::atoi(e)));  // experiments
                 for (int s = c.begin; s < c.begin + c.count; ++s) {
                     kmax = std::max(kmax, p->items[s].kdim);

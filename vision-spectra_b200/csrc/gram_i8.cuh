@@ -40,6 +40,8 @@ constexpr int kI8TileM = 128;  // UMMA M
 constexpr int kI8TileN = 64;   // UMMA N
 constexpr int kI8ChunkK = 64;  // bytes of K per pipeline stage (= SWIZZLE_64B span)
 constexpr int kI8Stages = 3;
+constexpr int kI8EpiWarps = 8;                    // two per TMEM lane quarter: 32 rows x 32 columns each
+constexpr int kI8Threads = 32 * (2 + kI8EpiWarps);  // + TMA producer + MMA issuer
 constexpr int kI8StageBytes = kDigits * (kI8TileM + kI8TileN) * kI8ChunkK;  // 73728
 constexpr int kI8SmemBytes = kI8Stages * kI8StageBytes + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int kI8MaxTiles = 64;
@@ -279,25 +281,47 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, int (&r)[16]) {
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
+// 16 TMEM lanes (rows) x 32 columns in the MMA-fragment distribution: lane l, register 4m + e + 2v holds
+// row (l >> 2) + 8 v, column 8 m + 2 (l & 3) + e  (m = 0..3, e = 0..1, v = 0..1).  Four lanes hold the eight columns of
+// a row: after conversion to FP64 a warp's registers (m, v) ARE one 8 x 8 tile of the Gram layout, 16 bytes per lane.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(unsigned taddr, int (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+// exact int32 -> double without the conversion unit: 2^52 + 2^31 + x has x + 2^31 in its low mantissa word
+__device__ __forceinline__ double i32_to_f64(int x) {
+    return __hiloint2double(0x43300000, x ^ 0x80000000) - 4503601774854144.0;  // 2^52 + 2^31
+}
 
 // ------------------------------------------------------------------------------------- MMA
-__global__ void __launch_bounds__(192, 1)
+// Persistent: one CTA per SM walks the work units (item, 128-row tile) u = blockIdx.x, + gridDim.x, ...; the three
+// roles run their own loops over the same unit / tile sequence and meet only at the mbarriers, whose phases count
+// chunks (ring) and tiles (accumulators) across units.  The seven level accumulators take 448 of the 512 TMEM
+// columns, so there is ONE accumulator set and the next tile's MMAs cannot start before the epilogue has read it:
+// the epilogue therefore drains the whole tile into registers first (64 FP64 values per thread, Horner in exact
+// integers on the way), releases TMEM, and only then scales and stores -- the stores of tile t, the launch
+// prologue and the TMEM allocation of a non-persistent CTA no longer sit between two tiles' MMAs.
+__global__ void __launch_bounds__(kI8Threads, 1)
     gram_i8_mma_kernel(const ItemDesc* __restrict__ items, I8Class cls, unsigned char* __restrict__ wsb,
                        double* __restrict__ ws, const __grid_constant__ CUtensorMap tmA,
                        const __grid_constant__ CUtensorMap tmB) {
     extern __shared__ unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int item = blockIdx.y;  // tiles of one matrix are adjacent in launch order: they share L2
-    const int mt = blockIdx.x;
-    const ItemDesc it = items[cls.begin + item];
-    const int n = it.n;
-    const int ntiles = cls.nt_count[mt];
+    const int units = cls.count * cls.mtiles;
+    // unit of this CTA in round r: rotated by r, so that with an even grid a CTA alternates between the 128-row tiles of a
+    // matrix (2 and 3 column tiles at n = 192) instead of always drawing the same one
+#define VSP_I8_UNIT(r, u)                                                        \
+    const int u = (r) * (int)gridDim.x + (int)((blockIdx.x + (r)) % gridDim.x); \
+    if (u >= units) continue
     const int nchunks = cls.kp / kI8ChunkK;
 
     unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(tiles + kI8Stages * kI8StageBytes);
-    // bars[0..2] full, [3..5] empty, [6] accumulators ready, [7] accumulators drained; then the TMEM base
-    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 8);
+    // bars[0..S) full, [S..2S) empty, [2S] accumulators ready, [2S+1] accumulators drained; then the TMEM base
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * kI8Stages + 2);
     const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + kI8Stages);
     const unsigned accbar = smem_u32(bars + 2 * kI8Stages), drainbar = smem_u32(bars + 2 * kI8Stages + 1);
 
@@ -307,7 +331,7 @@ __global__ void __launch_bounds__(192, 1)
             mbar_init(empty0 + 8 * s, 1);
         }
         mbar_init(accbar, 1);
-        mbar_init(drainbar, 4);  // one arrival per epilogue warp
+        mbar_init(drainbar, kI8EpiWarps);  // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // whole warp: allocate all 512 TMEM columns (7 levels x 64 used)
@@ -322,20 +346,26 @@ __global__ void __launch_bounds__(192, 1)
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            const int rowA = item * kDigits * n + mt * kI8TileM;  // + t*n per digit plane
-            int g = 0;                                            // chunk counter over all tiles
-            for (int nt = 0; nt < ntiles; ++nt) {
-                const int rowB = item * kDigits * n + nt * kI8TileN;
-                for (int c = 0; c < nchunks; ++c, ++g) {
-                    const int s = g % kI8Stages;
-                    if (g >= kI8Stages) mbar_wait(empty0 + 8 * s, ((g / kI8Stages) - 1) & 1);
-                    mbar_expect_tx(full0 + 8 * s, kI8StageBytes);
-                    const unsigned base = smem_u32(tiles + s * kI8StageBytes);
+            int g = 0;  // chunk counter over all tiles of all units
+            for (int rnd = 0; rnd * (int)gridDim.x < units; ++rnd) {
+                VSP_I8_UNIT(rnd, u);
+                const int item = u / cls.mtiles, mt = u - item * cls.mtiles;  // tiles of one matrix run on neighbouring SMs: L2
+                const int n = cls.n;
+                const int ntiles = cls.nt_count[mt];
+                const int rowA = item * kDigits * n + mt * kI8TileM;  // + t*n per digit plane
+                for (int nt = 0; nt < ntiles; ++nt) {
+                    const int rowB = item * kDigits * n + nt * kI8TileN;
+                    for (int c = 0; c < nchunks; ++c, ++g) {
+                        const int s = g % kI8Stages;
+                        if (g >= kI8Stages) mbar_wait(empty0 + 8 * s, ((g / kI8Stages) - 1) & 1);
+                        mbar_expect_tx(full0 + 8 * s, kI8StageBytes);
+                        const unsigned base = smem_u32(tiles + s * kI8StageBytes);
 #pragma unroll
-                    for (int t = 0; t < kDigits; ++t) {
-                        tma_load_2d(base + t * (kI8TileM * kI8ChunkK), &tmA, full0 + 8 * s, c * kI8ChunkK, rowA + t * n);
-                        tma_load_2d(base + kDigits * kI8TileM * kI8ChunkK + t * (kI8TileN * kI8ChunkK), &tmB,
-                                    full0 + 8 * s, c * kI8ChunkK, rowB + t * n);
+                        for (int t = 0; t < kDigits; ++t) {
+                            tma_load_2d(base + t * (kI8TileM * kI8ChunkK), &tmA, full0 + 8 * s, c * kI8ChunkK, rowA + t * n);
+                            tma_load_2d(base + kDigits * kI8TileM * kI8ChunkK + t * (kI8TileN * kI8ChunkK), &tmB,
+                                        full0 + 8 * s, c * kI8ChunkK, rowB + t * n);
+                        }
                     }
                 }
             }
@@ -348,139 +378,197 @@ __global__ void __launch_bounds__(192, 1)
                                    ((unsigned)(kI8TileM >> 4) << 24);
             const unsigned long long adesc0 = umma_desc_sw64(smem_u32(tiles));
             const unsigned long long bdesc0 = umma_desc_sw64(smem_u32(tiles) + kDigits * kI8TileM * kI8ChunkK);
-            int g = 0;
-            for (int ti = 0; ti < ntiles; ++ti) {
-                if (ti > 0) {  // the epilogue must have drained the accumulators of the previous tile
-                    mbar_wait(drainbar, (ti - 1) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                }
-                for (int c = 0; c < nchunks; ++c, ++g) {
-                    const int s = g % kI8Stages;
-                    mbar_wait(full0 + 8 * s, (g / kI8Stages) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    // descriptors differ from the stage-0 ones only in the 16-byte-granular start
-                    // address field: one 64-bit add per operand instead of rebuilding them
-                    const unsigned long long adS = adesc0 + (unsigned long long)(s * (kI8StageBytes >> 4));
-                    const unsigned long long bdS = bdesc0 + (unsigned long long)(s * (kI8StageBytes >> 4));
+            int g = 0, tile = 0;  // chunk / tile counters over all units
+#ifdef VSP_PHASE_TIMING
+            long long tm[3] = {0, 0, 0}, tk = clock64();
+#define VSP_GLAP(k) do { const long long now_ = clock64(); tm[k] += now_ - tk; tk = now_; } while (0)
+#else
+#define VSP_GLAP(k) ((void)0)
+#endif
+            for (int rnd = 0; rnd * (int)gridDim.x < units; ++rnd) {
+                VSP_I8_UNIT(rnd, u);
+                const int ntiles = cls.nt_count[u % cls.mtiles];
+                for (int ti = 0; ti < ntiles; ++ti, ++tile) {
+                    VSP_GLAP(2);
+                    if (tile > 0) {  // the epilogue must have drained the accumulators of the previous tile
+                        mbar_wait(drainbar, (tile - 1) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    VSP_GLAP(0);
+                    for (int c = 0; c < nchunks; ++c, ++g) {
+                        const int s = g % kI8Stages;
+                        VSP_GLAP(2);
+                        mbar_wait(full0 + 8 * s, (g / kI8Stages) & 1);
+                        VSP_GLAP(1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        // descriptors differ from the stage-0 ones only in the 16-byte-granular start
+                        // address field: one 64-bit add per operand instead of rebuilding them
+                        const unsigned long long adS = adesc0 + (unsigned long long)(s * (kI8StageBytes >> 4));
+                        const unsigned long long bdS = bdesc0 + (unsigned long long)(s * (kI8StageBytes >> 4));
 #pragma unroll
-                    for (int lv = 0; lv < kLevels; ++lv) {
-                        constexpr int kTop = kDigits - 1;
-                        const int tlo = lv > kTop ? lv - kTop : 0;
-                        const int thi = lv < kTop ? lv : kTop;
+                        for (int lv = 0; lv < kLevels; ++lv) {
+                            constexpr int kTop = kDigits - 1;
+                            const int tlo = lv > kTop ? lv - kTop : 0;
+                            const int thi = lv < kTop ? lv : kTop;
 #pragma unroll
-                        for (int t = 0; t < kDigits; ++t) {
-                            if (t < tlo || t > thi) continue;
+                            for (int t = 0; t < kDigits; ++t) {
+                                if (t < tlo || t > thi) continue;
 #pragma unroll
-                            for (int ks = 0; ks < kI8ChunkK / 32; ++ks) {
-                                const unsigned acc = (c > 0 || t > tlo || ks > 0) ? 1u : 0u;
-                                umma_i8(tmem_base + lv * kI8TileN,
-                                        adS + (unsigned long long)(((t * kI8TileM * kI8ChunkK) >> 4) + 2 * ks),
-                                        bdS + (unsigned long long)((((lv - t) * kI8TileN * kI8ChunkK) >> 4) + 2 * ks),
-                                        idesc, acc);
+                                for (int ks = 0; ks < kI8ChunkK / 32; ++ks) {
+                                    const unsigned acc = (c > 0 || t > tlo || ks > 0) ? 1u : 0u;
+                                    umma_i8(tmem_base + lv * kI8TileN,
+                                            adS + (unsigned long long)(((t * kI8TileM * kI8ChunkK) >> 4) + 2 * ks),
+                                            bdS + (unsigned long long)((((lv - t) * kI8TileN * kI8ChunkK) >> 4) + 2 * ks),
+                                            idesc, acc);
+                                }
                             }
                         }
+                        umma_commit(empty0 + 8 * s);  // the stage is free once these MMAs have read it
                     }
-                    umma_commit(empty0 + 8 * s);  // the stage is free once these MMAs have read it
+                    umma_commit(accbar);
                 }
-                umma_commit(accbar);
             }
+#ifdef VSP_PHASE_TIMING
+            VSP_GLAP(2);
+            if (blockIdx.x == 0)
+                printf("[gram mma kp=%d] tiles %d cycles: wait-drain %lld  wait-full %lld  issue %lld\n", cls.kp, tile, tm[0], tm[1], tm[2]);
+#endif
+#undef VSP_GLAP
         }
     } else {
-        // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
-        const int q = warp & 3;
-        const int i = mt * kI8TileM + 32 * q + lane;  // Gram row of this thread
-        const int* __restrict__ E = reinterpret_cast<const int*>(wsb + cls.exp_off) + (int64_t)item * n;
-        const int Ei = (i < n) ? E[i] : 1;
-        double* __restrict__ G = ws + it.gram_off;
-        // kGramTiled (sbr8.cuh): frame coordinates and the offsets that only depend on this thread's row
-        const int layout = it.full;
-        const int foff = ((n + 7) & ~7) - n, fi = i + foff, fI = fi >> 3;
-        const int frow = tile_off(fI, 0) + ((fi & 7) << 3);    // + 64 * tile column + column in tile
-        const int fdiag = tile_off(fI, fI) + (fi & 7);         // mirror inside the diagonal tile: + 8 * column in tile
-        if (layout == kGramTiled && foff > 0 && i < n) {       // the frame padding is zero
-            for (int c = 0; c < foff; ++c) G[frow + c] = 0.0;
-            if (i == 0)
-                for (int e = 0; e < 8 * foff; ++e) G[e] = 0.0;
-        }
-        for (int ti = 0; ti < ntiles; ++ti) {
-            const int nt = ti;
-            mbar_wait(accbar, ti & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-            for (int cc = 0; cc < kI8TileN / 16; ++cc) {
-                // Horner over the levels in exact 64-bit integers, split in two so nothing overflows:
-                //   hi = P0 128^2 + P1 128 + P2 (< 2^42),  lo = P3 128^3 + ... + P6 (< 2^49),
-                //   sum_s P_s 128^(6-s) = hi 2^28 + lo   -> two conversions and one FMA per element
-                double acc[16];
-                long long hi[16];
-                int r[16];
-                const unsigned taddr = tmem_base + ((unsigned)(32 * q) << 16) + cc * 16;
-                tmem_ld16(taddr, r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // ===== epilogue: warps 2..9.  A warp may read the TMEM lanes 32 (warp % 4) .. +31; the two warps of a lane
+        //       quarter split the 64 columns: 32 rows x 32 columns per warp and tile, 32 FP64 values per thread
+        const int q = warp & 3, ch = (warp - 2) >> 2;
+        const int lr = lane >> 2, lc = 2 * (lane & 3);  // row and first column of this lane inside an 8 x 8 tile
+        int tile = 0;
+#ifdef VSP_PHASE_TIMING
+        long long te[4] = {0, 0, 0, 0}, tk = clock64();
+#define VSP_ELAP(k) do { const long long now_ = clock64(); te[k] += now_ - tk; tk = now_; } while (0)
+#else
+#define VSP_ELAP(k) ((void)0)
+#endif
+        for (int rnd = 0; rnd * (int)gridDim.x < units; ++rnd) {
+            VSP_I8_UNIT(rnd, u);
+            const int item = u / cls.mtiles, mt = u - item * cls.mtiles;
+            const ItemDesc it = items[cls.begin + item];
+            const int n = it.n;
+            const int ntiles = cls.nt_count[mt];
+            const int* __restrict__ E = reinterpret_cast<const int*>(wsb + cls.exp_off) + (int64_t)item * n;
+            double* __restrict__ G = ws + it.gram_off;
+            const int layout = it.full;
+            const int foff = ((n + 7) & ~7) - n;  // kGramTiled (sbr8.cuh): frame offset of the top-left padding
+            if (layout == kGramTiled && foff > 0) {  // the frame padding is zero (one row per thread of warps 2..5)
+                const int i = mt * kI8TileM + (tid - 64);
+                if (tid - 64 < kI8TileM && i < n) {
+                    const int fi = i + foff;
+                    const int frow = tile_off(fi >> 3, 0) + ((fi & 7) << 3);
+                    for (int c = 0; c < foff; ++c) G[frow + c] = 0.0;
+                    if (i == 0)
+                        for (int e = 0; e < 8 * foff; ++e) G[e] = 0.0;
+                }
+            }
+            // rows of this thread: R(h, v) = row0 + 16 h + 8 v (h, v = 0..1); their exponents
+            const int row0 = mt * kI8TileM + 32 * q + lr;
+            int Er[4];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) hi[k] = r[k];
+            for (int k = 0; k < 4; ++k) Er[k] = (row0 + 8 * k < n) ? E[row0 + 8 * k] : 1;
+            const bool fast = layout == kGramTiled && foff == 0;  // n is a multiple of 8: a warp's (h, v, m) block is one tile
+            for (int ti = 0; ti < ntiles; ++ti, ++tile) {
+                const int col0 = ti * kI8TileN + 32 * ch + lc;  // columns of this thread: col0 + 8 m + e
+                int Ec[8];
 #pragma unroll
-                for (int lv = 1; lv < 3; ++lv) {
-                    tmem_ld16(taddr + lv * kI8TileN, r);
+                for (int k = 0; k < 8; ++k) Ec[k] = (col0 + 8 * (k >> 1) + (k & 1) < n) ? E[col0 + 8 * (k >> 1) + (k & 1)] : 1;
+                VSP_ELAP(3);
+                mbar_wait(accbar, tile & 1);
+                VSP_ELAP(0);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // ---- drain: all seven levels of 16 rows x 32 columns per wait; Horner in FP64 on exact integers, split
+                //   in two so that nothing is rounded before the last step:
+                //   hi = P0 128^2 + P1 128 + P2 (< 2^46),  lo = P3 128^3 + ... + P6 (< 2^53),  sum_s P_s 128^(6-s) = hi 2^28 + lo
+                double acc[32];  // [h][4 m + e + 2 v]
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const unsigned taddr = tmem_base + ((unsigned)(32 * q + 16 * h) << 16) + 32 * ch;
+                    int r[kLevels][16];
+#pragma unroll
+                    for (int lv = 0; lv < kLevels; ++lv) tmem_ld_16x256b_x4(taddr + lv * kI8TileN, r[lv]);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) hi[k] = hi[k] * 128 + r[k];
+                    for (int k = 0; k < 16; ++k) {
+                        const double hi = fma(fma(i32_to_f64(r[0][k]), 128.0, i32_to_f64(r[1][k])), 128.0, i32_to_f64(r[2][k]));
+                        const double lo = fma(fma(fma(i32_to_f64(r[3][k]), 128.0, i32_to_f64(r[4][k])), 128.0, i32_to_f64(r[5][k])),
+                                              128.0, i32_to_f64(r[6][k]));
+                        acc[16 * h + k] = fma(hi, 268435456.0, lo);  // 2^28
+                    }
                 }
+                // every level of this tile has been read: release TMEM to the next tile's MMAs
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(drainbar) : "memory");
+                VSP_ELAP(1);
+                // ---- scale and store: sum_k q_i q_j = 128^4 * acc ; x = q 2^(E-167)  ->  2^(Ei+Ej-334+28)
 #pragma unroll
-                for (int k = 0; k < 16; ++k) acc[k] = (double)hi[k] * 268435456.0;  // 2^28
-                tmem_ld16(taddr + 3 * kI8TileN, r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                for (int h = 0; h < 2; ++h) {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) hi[k] = r[k];
+                    for (int v = 0; v < 2; ++v) {
+                        const int R = row0 + 16 * h + 8 * v, Ei = Er[2 * h + v];
+                        const int I = (mt * kI8TileM + 32 * q + 16 * h + 8 * v) >> 3;  // tile row (warp-uniform)
 #pragma unroll
-                for (int lv = 4; lv < kLevels; ++lv) {
-                    tmem_ld16(taddr + lv * kI8TileN, r);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        for (int m = 0; m < 4; ++m) {
+                            const int J = (ti * kI8TileN + 32 * ch + 8 * m) >> 3;  // tile column (warp-uniform)
+                            double g[2];
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) hi[k] = hi[k] * 128 + r[k];
-                }
-#pragma unroll
-                for (int k = 0; k < 16; ++k) acc[k] += (double)hi[k];
-                if (cc == kI8TileN / 16 - 1) {  // every level of this tile has been read: release TMEM
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(drainbar) : "memory");
-                }
-                // column exponents of this 16-column group: one load per lane, then shuffles (a per-element global
-                // load here sits on the critical path between two tiles' MMAs)
-                const int jl = nt * kI8TileN + cc * 16 + (lane & 15);
-                const int Ejl = (jl < n) ? E[jl] : 1;
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const int Ej = __shfl_sync(0xffffffffu, Ejl, k);
-                    if (i < n) {
-                        const int j = nt * kI8TileN + cc * 16 + k;
-                        if (j <= i) {
-                            double g;
-                            if (Ei == 255 || Ej == 255) {
-                                g = __longlong_as_double(0x7ff8000000000000LL);  // NaN/Inf in the input row
-                            } else {
-                                // sum_k q_i q_j = 128^4 * acc ; x = q 2^(E-167)  ->  2^(Ei+Ej-334+28)
+                            for (int e = 0; e < 2; ++e) {
+                                const int Ej = Ec[2 * m + e];
                                 const int be = Ei + Ej - 306 + 1023;
-                                g = acc[k] * __hiloint2double(be << 20, 0);
+                                g[e] = (Ei == 255 || Ej == 255) ? __longlong_as_double(0x7ff8000000000000LL)  // NaN/Inf in the input row
+                                                                : acc[16 * h + 4 * m + 2 * v + e] * __hiloint2double(be << 20, 0);
                             }
-                            if (layout == kGramTiled) {
-                                const int fj = j + foff;
-                                G[frow + ((fj >> 3) << 6) + (fj & 7)] = g;
-                                if ((fj >> 3) == fI) G[fdiag + ((fj & 7) << 3)] = g;  // diagonal tile: both triangles
-                            } else if (layout == kGramFull) {
-                                G[(int64_t)i * n + j] = g;
-                                G[(int64_t)j * n + i] = g;
-                            } else {
-                                G[poff(i) + j] = g;
+                            if (fast) {
+                                if (8 * I >= n || J > I) continue;  // warp-uniform
+                                if (J == I) {
+                                    // diagonal tile: both triangles.  Position (lr, lc + e) above the diagonal takes the value
+                                    // of (lc + e, lr), held by lane 4 (lc + e) + (lr >> 1), component lr & 1
+#pragma unroll
+                                    for (int e = 0; e < 2; ++e) {
+                                        const int src = 4 * (lc + e) + (lr >> 1);
+                                        const double m0 = __shfl_sync(0xffffffffu, g[0], src), m1 = __shfl_sync(0xffffffffu, g[1], src);
+                                        if (lc + e > lr) g[e] = (lr & 1) ? m1 : m0;
+                                    }
+                                }
+                                // one 8 x 8 tile = 512 contiguous bytes per warp store
+                                *reinterpret_cast<double2*>(G + tile_off(I, J) + 2 * lane) = make_double2(g[0], g[1]);
+                            } else if (R < n) {
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    const int C = ti * kI8TileN + 32 * ch + 8 * m + lc + e;
+                                    if (C > R) continue;
+                                    if (layout == kGramTiled) {
+                                        const int fi = R + foff, fj = C + foff;
+                                        G[tile_off(fi >> 3, fj >> 3) + ((fi & 7) << 3) + (fj & 7)] = g[e];
+                                        if ((fj >> 3) == (fi >> 3)) G[tile_off(fi >> 3, fi >> 3) + ((fj & 7) << 3) + (fi & 7)] = g[e];
+                                    } else if (layout == kGramFull) {
+                                        G[(int64_t)R * n + C] = g[e];
+                                        G[(int64_t)C * n + R] = g[e];
+                                    } else {
+                                        G[poff(R) + C] = g[e];
+                                    }
+                                }
                             }
                         }
                     }
                 }
             }
         }
+#ifdef VSP_PHASE_TIMING
+        VSP_ELAP(2);
+        if (blockIdx.x == 0 && tid == 64)
+            printf("[gram epilogue kp=%d] tiles %d cycles: wait-acc %lld  drain %lld  store(last) %lld  setup+store %lld\n", cls.kp, tile, te[0], te[1], te[2], te[3]);
+#endif
+#undef VSP_ELAP
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
+#undef VSP_I8_UNIT
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

@@ -287,6 +287,20 @@ class SweepRunner:
         L = self.nlanes
         free = [None] * L  # event: slot's previous consumer finished
         keep = []
+        # results leave the pinned staging buffers chunk by chunk while later chunks are still in flight: only the last
+        # (short) chunks are copied out after the device has drained
+        rec = np.empty(nck * mats, dtype=nat.RECORD_DTYPE)
+        sv_out = np.empty(nck * n_sv, dtype=np.float64) if want_sv else None
+        rec_view = rec_host.numpy().view(nat.RECORD_DTYPE)
+        sv_view = sv_host.numpy() if want_sv else None
+        landed: list[tuple] = []  # (event after the chunk's D2H copies, c0, c1), in launch order
+
+        def unload(c0: int, c1: int) -> None:
+            rec[c0 * mats : c1 * mats] = rec_view[c0 * mats : c1 * mats]
+            rec["item"][c0 * mats : c1 * mats] += c0 * mats  # records carry chunk-local item ids
+            if want_sv:
+                sv_out[c0 * n_sv : c1 * n_sv] = sv_view[c0 * n_sv : c1 * n_sv]
+
         # chunk schedule: short chunks at both ends (the first chunk's copy and the last chunk's kernels are the only
         # parts of the step that do not overlap anything), full ones in between
         starts = self._chunk_starts(nck)
@@ -330,11 +344,16 @@ class SweepRunner:
                 if want_sv:
                     s0 = c0 * n_sv
                     sv_host[s0 : s0 + res.sv.numel()].copy_(res.sv, non_blocking=True)
+                home = torch.cuda.Event()
+                home.record(lane_stream)
+                landed.append((home, c0, c1))
             keep.append(res)
+            while landed and landed[0][0].query():
+                _, a0, a1 = landed.pop(0)
+                unload(a0, a1)
+        for home, a0, a1 in landed:
+            home.synchronize()
+            unload(a0, a1)
         for _, cs in self._lanes:
             main.wait_stream(cs)
-        main.synchronize()
-        rec = rec_host.numpy().view(nat.RECORD_DTYPE).copy()
-        for c0, c1 in zip(starts[:-1], starts[1:]):  # records carry chunk-local item ids
-            rec["item"][c0 * mats : c1 * mats] += c0 * mats
-        return rec, (sv_host.numpy().copy() if want_sv else None)
+        return rec, sv_out

@@ -249,11 +249,13 @@ class SweepRunner:
         return BatchResult(records, sv, offs, nck * mats)
 
     def _chunk_starts(self, nck: int) -> list[int]:
-        """Chunk boundaries of run_host: ramp up 1/4, 1/2 of a chunk, full chunks, ramp down 1/2, 1/4."""
+        """Chunk boundaries of run_host: ramp up 1/4, 1/2 of a chunk, full chunks, ramp down 1/2, 1/4, 1/8."""
         c = self.chunk
         if not self.ramp or nck < 4 * c or c < 4:
             return list(range(0, nck, c)) + [nck]
         head, tail = [c // 4, c // 2], [c // 2, c // 4]
+        if c >= 8:  # the step ends one chunk latency (~2 ms) after the last byte has landed: make that chunk a small one
+            tail.append(c // 8)
         mid = nck - sum(head) - sum(tail)
         full, rem = divmod(mid, c)
         body = [c] * full

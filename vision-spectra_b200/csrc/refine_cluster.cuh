@@ -27,7 +27,7 @@
 namespace vsp {
 
 constexpr int kRcThreads = 512;
-constexpr int kRcMaxCluster = 8;
+constexpr int kRcMaxCluster = 16;  // above 8: non-portable cluster size (opt-in per kernel; one GPC holds 16+ SMs on B200)
 
 // pool slot layout (doubles): X [B shares of ceil(n / B) columns][K] | 2 x exchange { scal [B][8] | ypart [B][K] | col [K] }
 __host__ __device__ inline int64_t refine_cluster_x_doubles(int64_t K, int64_t n, int B) { return K * (((n + B - 1) / B) * B); }

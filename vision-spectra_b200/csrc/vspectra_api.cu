@@ -426,6 +426,8 @@ static int plan_layout(vsp_plan* p, int32_t count, const int32_t* rows, const in
                 // n <= 256: THREE CTAs per matrix.  A 192 x 192 share is then exactly the 96 KB shared-memory cap, and the
                 // co-residency limit (clusters do not span GPCs) is ~46 clusters instead of ~33: the Scenario-A sweep flags
                 // 36 matrices per step, which four-CTA clusters served in two rounds (re-solve 3.6 ms, three-CTA 2.3 ms)
+                // n > 256: sixteen CTAs (non-portable cluster size, one GPC): a step sweeps the CTA's share of X in L2 three
+                // times, so the step time follows the share: n = 768 re-solve 29 -> 19 ms with 16 instead of 8 CTAs
                 int B = c.n <= 256 ? 3 : kRcMaxCluster;
                 if (const char* e = std::getenv("VSP_REFINE_B")) B = std::max(1, std::min(kRcMaxCluster, std::atoi(e)));  // experiments
                 for (int s = c.begin; s < c.begin + c.count; ++s) {
@@ -723,6 +725,7 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
         VSP_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(csmem, 48 * 1024))); \
         if (shared)                                                                                                     \
             VSP_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+        if (B > 8) VSP_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));           \
         VSP_CUDA(cudaLaunchKernelEx(&cfg, KERNEL, (const ItemDesc*)p->d_items, gate, pool, c.npad, Kpad, nloc, c.refine_xs_cap, \
                                     p->opts, d_sv, d_records, d_dist));                                                 \
     }

@@ -397,34 +397,55 @@ def extra_scenario(eng, dev, key: str, sync_all, steps: int = 3) -> dict:
 def extra_vit_base_stress(eng, dev, sync_all, ckpts: int = 16, chunk: int = 4) -> dict:
     """BASELINE.json configs[4]: ViT-Base 768d/12L random-init checkpoints (72 matrices each, up to 768x3072), analysed
     in chunks of `chunk` checkpoints (1.36 GB of inputs per chunk, regenerated per chunk: 10 000 checkpoints would be
-    3.4 TB).  Reports matrices/s of this rank and the stage times / FP64 roofline of the n = 768 reduction."""
+    3.4 TB).  Chunks alternate between two lanes (engine + stream + arena set each) and a chunk's records are read one
+    chunk later, so the re-solve tail of chunk i (19 ms on a few 16-CTA clusters) runs beside chunk i+1's reduction.
+    Reports matrices/s of this rank and the stage times / FP64 roofline of the n = 768 reduction."""
     import torch
 
+    from vision_spectra_b200.engine import SpectraEngine
     from vision_spectra_b200.sweep import CheckpointLayout, SweepRunner
 
     lay = CheckpointLayout.vit(768, 12)
-    runner = SweepRunner(eng, lay)
     g = torch.Generator(device=dev).manual_seed(768)
-    arenas = [torch.randn(lay.arena_elems, generator=g, device=dev, dtype=torch.float32) * 0.02 for _ in range(chunk)]
-    runner.run_device(arenas, want_sv=True)  # warm-up (plan, workspace)
+    lanes = []
+    for k in range(2):
+        lane_eng = eng if k == 0 else SpectraEngine(dev)
+        arenas = [torch.randn(lay.arena_elems, generator=g, device=dev, dtype=torch.float32) * 0.02 for _ in range(chunk)]
+        lanes.append((SweepRunner(lane_eng, lay), torch.cuda.Stream(device=dev), arenas))
+    for runner, stream, arenas in lanes:  # warm-up (plan, workspace)
+        with torch.cuda.stream(stream):
+            runner.run_device(arenas, want_sv=True)
     sync_all()
+    main = torch.cuda.current_stream(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     refined = 0
+    pending = None
     e0.record()
-    for c in range(0, ckpts, chunk):
-        for a in arenas:  # the next chunk's checkpoints (device-side generation is part of the chunk loop, not of the metric)
-            a.normal_(0.0, 0.02, generator=g)
-        res = runner.run_device(arenas, want_sv=True)
-        refined += int((res.records_host()["status"] == 96).sum())
+    for s in (l[1] for l in lanes):
+        s.wait_stream(main)
+    for ci, c in enumerate(range(0, ckpts, chunk)):
+        runner, stream, arenas = lanes[ci % 2]
+        with torch.cuda.stream(stream):
+            for a in arenas:  # the next chunk's checkpoints (device-side generation is part of the chunk loop, not of the metric)
+                a.normal_(0.0, 0.02, generator=g)
+            res = runner.run_device(arenas, want_sv=True)
+        if pending is not None:
+            with torch.cuda.stream(pending[1]):
+                refined += int((pending[0].records_host()["status"] == 96).sum())
+        pending = (res, stream)
+    with torch.cuda.stream(pending[1]):
+        refined += int((pending[0].records_host()["status"] == 96).sum())
+    for s in (l[1] for l in lanes):
+        main.wait_stream(s)
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
     sm: list = []
-    runner.run_device(arenas, want_sv=True, stage_ms=sm)
+    lanes[0][0].run_device(lanes[0][2], want_sv=True, stage_ms=sm)
     sync_all()
     n = ckpts * lay.matrices
     flops = chunk * lay.flops_tridiag()
-    return {"workload": f"ViT-Base 768d/12L, {ckpts} checkpoints in chunks of {chunk}", "matrices": n, "ms": ms,
+    return {"workload": f"ViT-Base 768d/12L, {ckpts} checkpoints in chunks of {chunk}, two lanes", "matrices": n, "ms": ms,
             "matrices_per_s": n / (ms / 1e3), "refined": refined, "per_rank": True,
             "stage_ms_per_chunk": {"gram": sm[0], "reduction": sm[1], "bisect_refine": sm[2]},
             "reduction_tflops": flops / 1e12 / (sm[1] / 1e3), "note": "timed region includes regenerating each chunk's weights on the device"}

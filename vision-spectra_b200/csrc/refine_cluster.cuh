@@ -44,7 +44,9 @@ __host__ __device__ inline size_t refine_cluster_tail_doubles(int npad) { return
 
 #if defined(__CUDACC__)
 
-template <typename TIn>
+// WIDE: the CTA's share of X lives in L2 (n > 256): the sweeps keep eight independent loads per lane in flight (an L2
+// round trip is ~700 cycles; with the default unrolling a step of n = 768 moved 23 GB/s per SM)
+template <typename TIn, bool WIDE>
 __device__ __forceinline__ void refine_cluster_body(const ItemDesc* __restrict__ items, RefineGate gate, RefinePool pool, int npad,
                                                     int Kpad, int nloc_max, int xs_cap, vsp_opts opts, double* __restrict__ sv_out,
                                                     vsp_record* __restrict__ records, double* __restrict__ dist_out) {
@@ -144,9 +146,33 @@ __device__ __forceinline__ void refine_cluster_body(const ItemDesc* __restrict__
                 double w = 0.0;
                 if (tau != 0.0) {
                     double dot = 0.0;
-                    for (int r = j + 1 + lane; r < K; r += 32) dot += vs[r] * cc[r];
-                    w = tau * (ctx.warp_sum(dot) + cj);
-                    for (int r = j + 1 + lane; r < K; r += 32) cc[r] -= w * vs[r];
+                    if constexpr (WIDE) {
+                        double d[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                        int r = j + 1 + lane;
+                        for (; r + 7 * 32 < K; r += 8 * 32) {
+                            double x[8];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) x[q] = cc[r + 32 * q];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) d[q] = fma(vs[r + 32 * q], x[q], d[q]);
+                        }
+                        for (; r < K; r += 32) d[0] = fma(vs[r], cc[r], d[0]);
+                        dot = ((d[0] + d[1]) + (d[2] + d[3])) + ((d[4] + d[5]) + (d[6] + d[7]));
+                        w = tau * (ctx.warp_sum(dot) + cj);
+                        r = j + 1 + lane;
+                        for (; r + 7 * 32 < K; r += 8 * 32) {
+                            double x[8];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) x[q] = cc[r + 32 * q];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) cc[r + 32 * q] = fma(-w, vs[r + 32 * q], x[q]);
+                        }
+                        for (; r < K; r += 32) cc[r] -= w * vs[r];
+                    } else {
+                        for (int r = j + 1 + lane; r < K; r += 32) dot += vs[r] * cc[r];
+                        w = tau * (ctx.warp_sum(dot) + cj);
+                        for (int r = j + 1 + lane; r < K; r += 32) cc[r] -= w * vs[r];
+                    }
                 }
                 if (lane == 0) rowj[lc] = cj - w;
                 if (c >= j + 2) s2 += (cj - w) * (cj - w);  // uniform over the warp
@@ -174,7 +200,21 @@ __device__ __forceinline__ void refine_cluster_body(const ItemDesc* __restrict__
                 if (G == 1) {
                     for (int r = j + 1 + tid; r < K; r += kRcThreads) {
                         double y = 0.0;
-                        for (int lc = lc2; lc < nloc; ++lc) y += Xl[(int64_t)lc * K + r] * rowj[lc];
+                        if constexpr (WIDE) {
+                            double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                            int lc = lc2;
+                            for (; lc + 7 < nloc; lc += 8) {
+                                double x[8];
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) x[q] = Xl[(int64_t)(lc + q) * K + r];
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) a[q] = fma(x[q], rowj[lc + q], a[q]);
+                            }
+                            for (; lc < nloc; ++lc) a[0] = fma(Xl[(int64_t)lc * K + r], rowj[lc], a[0]);
+                            y = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+                        } else {
+                            for (int lc = lc2; lc < nloc; ++lc) y += Xl[(int64_t)lc * K + r] * rowj[lc];
+                        }
                         ypart[(int64_t)rank * K + r] = y;
                     }
                 } else {  // G * nrows <= kRcThreads
@@ -236,7 +276,19 @@ __device__ __forceinline__ void refine_cluster_body(const ItemDesc* __restrict__
                 for (int lc = lcf + warp; lc < nloc; lc += NWARP) {
                     double* cc = Xl + (int64_t)lc * K;
                     const double u = us[lc];
-                    for (int r = j + 1 + lane; r < K; r += 32) cc[r] -= ys[r] * u;
+                    if constexpr (WIDE) {
+                        int r = j + 1 + lane;
+                        for (; r + 7 * 32 < K; r += 8 * 32) {
+                            double x[8];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) x[q] = cc[r + 32 * q];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) cc[r + 32 * q] = fma(-u, ys[r + 32 * q], x[q]);
+                        }
+                        for (; r < K; r += 32) cc[r] -= ys[r] * u;
+                    } else {
+                        for (int r = j + 1 + lane; r < K; r += 32) cc[r] -= ys[r] * u;
+                    }
                 }
             }
             __syncthreads();
@@ -295,14 +347,14 @@ __global__ void __launch_bounds__(kRcThreads)
     refine_cluster_kernel(const ItemDesc* __restrict__ items, RefineGate gate, RefinePool pool, int npad, int Kpad, int nloc_max,
                           int xs_cap, vsp_opts opts, double* __restrict__ sv_out, vsp_record* __restrict__ records,
                           double* __restrict__ dist_out) {
-    refine_cluster_body<TIn>(items, gate, pool, npad, Kpad, nloc_max, xs_cap, opts, sv_out, records, dist_out);
+    refine_cluster_body<TIn, true>(items, gate, pool, npad, Kpad, nloc_max, xs_cap, opts, sv_out, records, dist_out);
 }
 template <typename TIn>
 __global__ void __maxnreg__(64)
     refine_cluster_shared_kernel(const ItemDesc* __restrict__ items, RefineGate gate, RefinePool pool, int npad, int Kpad,
                                  int nloc_max, int xs_cap, vsp_opts opts, double* __restrict__ sv_out,
                                  vsp_record* __restrict__ records, double* __restrict__ dist_out) {
-    refine_cluster_body<TIn>(items, gate, pool, npad, Kpad, nloc_max, xs_cap, opts, sv_out, records, dist_out);
+    refine_cluster_body<TIn, false>(items, gate, pool, npad, Kpad, nloc_max, xs_cap, opts, sv_out, records, dist_out);
 }
 
 #endif  // __CUDACC__

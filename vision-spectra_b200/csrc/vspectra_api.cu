@@ -90,6 +90,7 @@ struct ShapeClass {
     int64_t refine_items_off;     // byte offset of the slot -> item table
     int refine_counter;           // index of this class's slot counter
     int refine_B;                 // CTAs per cluster of the re-solve (0: one-CTA kernel)
+    mutable int refine_launch_slots = 0;  // clusters per launch: refine_slots capped by what is resident at once (first execution)
     int refine_kmax;              // largest contraction length of the class
     int refine_xs_cap;            // doubles of shared memory for a CTA's share of X
 };
@@ -426,9 +427,10 @@ static int plan_layout(vsp_plan* p, int32_t count, const int32_t* rows, const in
                 // n <= 256: THREE CTAs per matrix.  A 192 x 192 share is then exactly the 96 KB shared-memory cap, and the
                 // co-residency limit (clusters do not span GPCs) is ~46 clusters instead of ~33: the Scenario-A sweep flags
                 // 36 matrices per step, which four-CTA clusters served in two rounds (re-solve 3.6 ms, three-CTA 2.3 ms)
-                // n > 256: sixteen CTAs (non-portable cluster size, one GPC): a step sweeps the CTA's share of X in L2 three
-                // times, so the step time follows the share: n = 768 re-solve 29 -> 19 ms with 16 instead of 8 CTAs
-                int B = c.n <= 256 ? 3 : kRcMaxCluster;
+                // n > 256: a step sweeps the CTA's share of X in L2 three times, so the step time follows the share: sixteen
+                // CTAs (non-portable cluster size, one GPC each: 8 resident clusters; n = 768: 14.8 ms per matrix) while the
+                // flagged matrices of a random-init class (~4 %) fit one round, else eight (22 ms, but 25 % fewer SM-ms)
+                int B = c.n <= 256 ? 3 : (c.count <= 200 ? kRcMaxCluster : 8);
                 if (const char* e = std::getenv("VSP_REFINE_B")) B = std::max(1, std::min(kRcMaxCluster, std::atoi(e)));  // experiments
                 for (int s = c.begin; s < c.begin + c.count; ++s) {
                     kmax = std::max(kmax, p->items[s].kdim);
@@ -726,6 +728,15 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
         if (shared)                                                                                                     \
             VSP_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
         if (B > 8) VSP_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));           \
+        if (c.refine_launch_slots == 0) {                                                                               \
+            /* no more clusters than are resident at once: a cluster that cannot be placed (a 16-CTA cluster needs a */ \
+            /* whole GPC) keeps the bisection kernel behind it out of the SMs until it has been dispatched           */ \
+            int active = 0;                                                                                             \
+            VSP_CUDA(cudaOccupancyMaxActiveClusters(&active, KERNEL, &cfg));                                            \
+            c.refine_launch_slots = std::max(1, std::min(c.refine_slots, active));                                      \
+        }                                                                                                               \
+        pool.slots = c.refine_launch_slots;                                                                             \
+        cfg.gridDim = dim3((unsigned)(B * c.refine_launch_slots));                                                      \
         VSP_CUDA(cudaLaunchKernelEx(&cfg, KERNEL, (const ItemDesc*)p->d_items, gate, pool, c.npad, Kpad, nloc, c.refine_xs_cap, \
                                     p->opts, d_sv, d_records, d_dist));                                                 \
     }

@@ -36,8 +36,19 @@ __host__ __device__ inline int64_t refine_cluster_slot_doubles(int64_t K, int64_
     return refine_cluster_x_doubles(K, n, B) + 2 * refine_cluster_ex_doubles(K, B) + 8;
 }
 // shared memory (doubles): reduction scratch | dq eq [npad] | v y [Kpad] | part [kRcThreads] | u rowj [nlocpad] | X share
-__host__ __device__ inline size_t refine_cluster_fixed_doubles(int npad, int Kpad, int nloc) {
-    return (size_t)CtaCtx::kScratchDoubles + 2 * (size_t)npad + 2 * (size_t)Kpad + kRcThreads + 2 * (size_t)((nloc + 3) & ~3) + 8;
+// FUSED (K <= 32 RPL): the right update of step j-1 and the left reflector of step j are ONE sweep over the CTA's
+// columns (a column's rows live in RPL registers per lane between its load and its store) instead of two sweeps with
+// four passes.  n > 256 entry point only (n = 768: 14.8 -> 11.6 ms per matrix).  At 64 registers (n <= 256 entry point)
+// the sweep spills and the re-solve slowed from 2.25 to 2.35 ms; with y' folded in as well (FUSEY: per-warp partial
+// y' through shared memory) to 2.44 ms: RPL = 0 there.
+constexpr int kRcRplWide = 24;  // K <= 768
+__host__ __device__ inline size_t refine_cluster_ypw_doubles(bool shared_variant) {
+    (void)shared_variant;
+    return 0;  // FUSEY is off in both entry points
+}
+__host__ __device__ inline size_t refine_cluster_fixed_doubles(int npad, int Kpad, int nloc, bool shared_variant) {
+    return (size_t)CtaCtx::kScratchDoubles + 2 * (size_t)npad + 2 * (size_t)Kpad + kRcThreads + 2 * (size_t)((nloc + 3) & ~3) + 8 +
+           refine_cluster_ypw_doubles(shared_variant);
 }
 // rank 0 re-uses everything behind the reduction scratch for the bisection: lam [npad] | part | DE [2 npad] | counter
 __host__ __device__ inline size_t refine_cluster_tail_doubles(int npad) { return (size_t)CtaCtx::kScratchDoubles + 7 * (size_t)npad + 16; }
@@ -46,7 +57,7 @@ __host__ __device__ inline size_t refine_cluster_tail_doubles(int npad) { return
 
 // WIDE: the CTA's share of X lives in L2 (n > 256): the sweeps keep eight independent loads per lane in flight (an L2
 // round trip is ~700 cycles; with the default unrolling a step of n = 768 moved 23 GB/s per SM)
-template <typename TIn, bool WIDE>
+template <typename TIn, bool WIDE, int RPL, bool FUSEY>
 __device__ __forceinline__ void refine_cluster_body(const ItemDesc* __restrict__ items, RefineGate gate, RefinePool pool, int npad,
                                                     int Kpad, int nloc_max, int xs_cap, vsp_opts opts, double* __restrict__ sv_out,
                                                     vsp_record* __restrict__ records, double* __restrict__ dist_out) {
@@ -67,7 +78,8 @@ __device__ __forceinline__ void refine_cluster_body(const ItemDesc* __restrict__
     double* part = ys + Kpad;     // [kRcThreads] column-group partial sums of the y' pass
     double* us = part + kRcThreads;  // [nloc] right reflector entries of the local columns
     double* rowj = us + ((nloc_max + 3) & ~3);  // [nloc] updated row j of the local columns
-    double* Xs = rowj + ((nloc_max + 3) & ~3) + 8;
+    double* ypw = rowj + ((nloc_max + 3) & ~3) + 8;  // [NWARP][32 RPL] partial y' of the warps (FUSEY)
+    double* Xs = ypw + (FUSEY ? (size_t)(kRcThreads / 32) * 32 * RPL : 0);
 
     const int nflagged = *gate.counter;
     for (int entry = slot; entry < nflagged; entry += pool.slots) {  // uniform over the cluster
@@ -83,6 +95,8 @@ __device__ __forceinline__ void refine_cluster_body(const ItemDesc* __restrict__
         // the CTA's share of the slot's global copy
         const int nshare = (n + B - 1) / B;
         double* Xl = ((int64_t)nshare * K <= (int64_t)xs_cap) ? Xs : Xg + (int64_t)rank * nshare * K;
+        const bool fused = RPL > 0 && K <= 32 * RPL;  // uniform over the cluster
+        bool pending = false;                         // fused: the right update of the previous step has not been applied yet
 
         // ---- scale by a power of two so that max |x| is in [0.5, 1): cluster-wide maximum
         double mx = 0.0;
@@ -139,6 +153,61 @@ __device__ __forceinline__ void refine_cluster_body(const ItemDesc* __restrict__
             // apply to the local columns c > j (one warp per column); collect the new row j and |row j|^2 (c >= j+2)
             const int lcf = (j + 1 - rank + B - 1) / B;  // first local column with c >= j + 1
             double s2 = 0.0;
+            if (fused) {
+                if constexpr (RPL > 0) {
+                    // ---- one sweep: right update of step j-1 (pending), left reflector of step j, partial y' of step j.
+                    //      Lane l, slot i holds row j + l + 32 i of the column between its load and its store.
+                    double yacc[FUSEY ? RPL : 1];
+#pragma unroll
+                    for (int i = 0; i < (FUSEY ? RPL : 1); ++i) yacc[i] = 0.0;
+                    for (int lc = lcf + warp; lc < nloc; lc += NWARP) {
+                        const int c = rank + B * lc;
+                        double* cc = Xl + (int64_t)lc * K;
+                        double x[RPL];
+#pragma unroll
+                        for (int i = 0; i < RPL; ++i) {
+                            const int r = j + lane + 32 * i;
+                            x[i] = (r < K) ? cc[r] : 0.0;
+                        }
+                        if (pending) {
+                            const double u = us[lc];
+#pragma unroll
+                            for (int i = 0; i < RPL; ++i) {
+                                const int r = j + lane + 32 * i;
+                                if (r < K) x[i] = fma(-u, ys[r], x[i]);
+                            }
+                        }
+                        const double cj = __shfl_sync(0xffffffffu, x[0], 0);  // row j
+                        double dot = 0.0;
+#pragma unroll
+                        for (int i = 0; i < RPL; ++i) {
+                            const int r = j + lane + 32 * i;
+                            if (r > j && r < K) dot = fma(vs[r], x[i], dot);
+                        }
+                        const double w = tau * (ctx.warp_sum(dot) + cj);
+                        const double rj = cj - w;
+                        const bool tail = c >= j + 2;  // uniform over the warp
+#pragma unroll
+                        for (int i = 0; i < RPL; ++i) {
+                            const int r = j + lane + 32 * i;
+                            if (r > j && r < K) {
+                                x[i] = fma(-w, vs[r], x[i]);
+                                cc[r] = x[i];
+                                if constexpr (FUSEY)
+                                    if (tail) yacc[i] = fma(x[i], rj, yacc[i]);
+                            }
+                        }
+                        if (lane == 0) rowj[lc] = rj;
+                        if (tail) s2 += rj * rj;
+                    }
+                    if constexpr (FUSEY) {
+#pragma unroll
+                        for (int i = 0; i < RPL; ++i)
+                            if (lane + 32 * i < K - j) ypw[warp * (32 * RPL) + lane + 32 * i] = yacc[i];
+                    }
+                    pending = false;
+                }
+            } else
             for (int lc = lcf + warp; lc < nloc; lc += NWARP) {
                 const int c = rank + B * lc;
                 double* cc = Xl + (int64_t)lc * K;
@@ -190,7 +259,14 @@ __device__ __forceinline__ void refine_cluster_body(const ItemDesc* __restrict__
             double* colx = ypart + (int64_t)B * K;
             const int own1 = (j + 1) % B;  // owner of column j + 1
             const int lc2 = (j + 2 - rank + B - 1) / B;  // first local column with c >= j + 2
-            {
+            if (FUSEY && fused) {
+                for (int sl = 1 + tid; sl < K - j; sl += kRcThreads) {  // slot sl <-> row j + sl
+                    double y = 0.0;
+#pragma unroll
+                    for (int wq = 0; wq < NWARP; ++wq) y += ypw[wq * (32 * RPL) + sl];
+                    ypart[(int64_t)rank * K + j + sl] = y;
+                }
+            } else {
                 // rows r > j, split over G column groups so that every thread has work
                 const int nrows = K - (j + 1);
                 int G = kRcThreads / (nrows > 0 ? nrows : 1);
@@ -271,7 +347,9 @@ __device__ __forceinline__ void refine_cluster_body(const ItemDesc* __restrict__
             for (int lc = lcf + tid; lc < nloc; lc += kRcThreads) us[lc] = (rank + B * lc == j + 1) ? 1.0 : rowj[lc] * usc;
             __syncthreads();
             VSP_RLAP(4);
-            if (tau2 != 0.0) {  // uniform over the cluster
+            if (fused) {
+                pending = tau2 != 0.0;  // applied by the next step's sweep
+            } else if (tau2 != 0.0) {  // uniform over the cluster
                 // rank-one update of the local columns c >= j+1, one warp per column
                 for (int lc = lcf + warp; lc < nloc; lc += NWARP) {
                     double* cc = Xl + (int64_t)lc * K;
@@ -347,14 +425,14 @@ __global__ void __launch_bounds__(kRcThreads)
     refine_cluster_kernel(const ItemDesc* __restrict__ items, RefineGate gate, RefinePool pool, int npad, int Kpad, int nloc_max,
                           int xs_cap, vsp_opts opts, double* __restrict__ sv_out, vsp_record* __restrict__ records,
                           double* __restrict__ dist_out) {
-    refine_cluster_body<TIn, true>(items, gate, pool, npad, Kpad, nloc_max, xs_cap, opts, sv_out, records, dist_out);
+    refine_cluster_body<TIn, true, kRcRplWide, false>(items, gate, pool, npad, Kpad, nloc_max, xs_cap, opts, sv_out, records, dist_out);
 }
 template <typename TIn>
 __global__ void __maxnreg__(64)
     refine_cluster_shared_kernel(const ItemDesc* __restrict__ items, RefineGate gate, RefinePool pool, int npad, int Kpad,
                                  int nloc_max, int xs_cap, vsp_opts opts, double* __restrict__ sv_out,
                                  vsp_record* __restrict__ records, double* __restrict__ dist_out) {
-    refine_cluster_body<TIn, false>(items, gate, pool, npad, Kpad, nloc_max, xs_cap, opts, sv_out, records, dist_out);
+    refine_cluster_body<TIn, false, 0, false>(items, gate, pool, npad, Kpad, nloc_max, xs_cap, opts, sv_out, records, dist_out);
 }
 
 #endif  // __CUDACC__

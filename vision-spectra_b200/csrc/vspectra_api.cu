@@ -706,7 +706,7 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
             VSP_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
             if (c.refine_B > 0) {
                 const int B = c.refine_B, Kpad = round_up(c.refine_kmax, 4), nloc = (c.n + B - 1) / B;
-                const size_t smem_d = std::max(refine_cluster_fixed_doubles(c.npad, Kpad, nloc) + (size_t)c.refine_xs_cap,
+                const size_t smem_d = std::max(refine_cluster_fixed_doubles(c.npad, Kpad, nloc, c.n <= 256) + (size_t)c.refine_xs_cap,
                                                refine_cluster_tail_doubles(c.npad));
                 const size_t csmem = smem_d * sizeof(double);
                 cudaLaunchConfig_t cfg = {};

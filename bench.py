@@ -73,7 +73,7 @@ def measure_i8_peak():
 
 
 def load_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r01_traffic.json)."""
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (latest profiles/r*_traffic.json)."""
     try:
         cand = sorted((ROOT / "profiles").glob("r*_traffic.json"))
         t = json.loads(cand[-1].read_text())

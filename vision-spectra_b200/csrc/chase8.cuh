@@ -2,7 +2,7 @@
 // Bd[r * 9 + j] = A[r][r - j] in frame indices) -> tridiagonal (d, e) by Householder bulge chasing.
 //
 // One CTA of kChase8Groups / 4 warps per matrix.  The working band (bandwidth grows to 15 while bulges are in flight) lives in shared memory
-// as L[r][jj] = B[r][r - jj], jj = 0..15, row stride 17, with 24 zero rows of padding so that the blocks at the bottom
+// as L[r][jj] = B[r][r - jj], jj = 0..15, row stride 17, with 14 zero rows of padding so that the blocks at the bottom
 // of the matrix need no special cases (a reflector built from zeros is the identity).
 //
 // Sweep k (k = 0..n-3) annihilates column k below the sub-diagonal; its step j works on the rows R = [r0, r0 + 7],
@@ -29,13 +29,13 @@
 namespace vsp {
 
 constexpr int kChase8W = 17;        // row stride: 16 stored diagonals + 1 pad
-constexpr int kChase8PadRows = 24;  // 3 b
+constexpr int kChase8PadRows = 14;  // a step reads the rows r0 .. r0 + 15 with r0 <= n - 2; 14 (not 3 b = 24) makes n = 192 fit EIGHT CTAs per SM
 constexpr int kChase8Groups = 8;    // eight-lane groups per matrix (two warps)
 constexpr int kChase8Threads = 8 * kChase8Groups;
 constexpr int kChase8Lag = 3;
 
 __host__ __device__ inline size_t chase8_smem_bytes(int n) {
-    return sizeof(double) * ((size_t)(n + kChase8PadRows) * kChase8W + 4 * kChase8Groups);
+    return sizeof(double) * ((size_t)(n + kChase8PadRows) * kChase8W + kChase8Groups);  // + progress table [2][groups] ints
 }
 
 // dot product of two 8-vectors as two chains of four (half the dependent latency of one chain, one more instruction)
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kChase8Threads)
     const int off = sbr8_order(n) - n;
     const int rows = n + kChase8PadRows;
     double* L = smem;
-    // progress table, double-buffered by tick parity: [2][groups][k, j, active, pad] -- a group reads its predecessor's
+    // progress table, double-buffered by tick parity: [2][groups] words k | j << 16 | active << 24 -- a group reads its predecessor's
     // entry of the previous tick while everybody writes this tick's, so one barrier per tick is enough
     int* prog = reinterpret_cast<int*>(L + (size_t)rows * kChase8W);
     double* out = ws + it.de_off;
@@ -79,18 +79,14 @@ __global__ void __launch_bounds__(kChase8Threads)
     const unsigned gmask = 0xffu << (lane & 24);
     int k = g, j = 0;
     bool active = g <= n - 3;
-    if (q == 0) {
-        prog[4 * g + 0] = k;
-        prog[4 * g + 1] = j;
-        prog[4 * g + 2] = active ? 1 : 0;
-    }
+    if (q == 0) prog[g] = k | (j << 16) | (active ? 1 << 24 : 0);
     int par = 0;
     while (__syncthreads_or(active)) {  // the barrier also orders last tick's stores and progress entries
         bool ready = false;
         if (active) {
             const int pg = (g + kChase8Groups - 1) % kChase8Groups;
-            const int* pp = prog + 4 * kChase8Groups * par + 4 * pg;
-            const int kp = pp[0], jp = pp[1], ap = pp[2];
+            const int pv = prog[kChase8Groups * par + pg];
+            const int kp = pv & 0xffff, jp = (pv >> 16) & 0xff, ap = pv >> 24;
             ready = (k == 0) || (ap == 0) || (kp > k - 1) || (kp == k - 1 && jp >= j + kChase8Lag);
         }
         par ^= 1;
@@ -191,10 +187,7 @@ __global__ void __launch_bounds__(kChase8Threads)
             }
         }
         if (q == 0) {  // every tick, ready or not: the other buffer is one tick old
-            int* pw = prog + 4 * kChase8Groups * par + 4 * g;
-            pw[0] = k;
-            pw[1] = j;
-            pw[2] = active ? 1 : 0;
+            prog[kChase8Groups * par + g] = k | (j << 16) | (active ? 1 << 24 : 0);
         }
     }
     if (tid >= 32) return;  // warp 0 publishes

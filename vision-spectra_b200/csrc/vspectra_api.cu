@@ -612,6 +612,7 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
             const size_t csm = chase8_smem_bytes(c.n);
             VSP_CUDA(cudaFuncSetAttribute(chase8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)std::max<size_t>(csm, 48 * 1024)));
+            VSP_CUDA(cudaFuncSetAttribute(chase8_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             chase8_kernel<<<c.count, kChase8Threads, csm, st>>>(p->d_items, c.begin, c.count, ws, gate);
         } else if (c.full == kGramPacked) {
             // two-stage reduction: blocked Householder to bandwidth 4 (sbr_band.cuh), bulge chasing (band_tridiag.cuh).

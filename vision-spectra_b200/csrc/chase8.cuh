@@ -77,14 +77,18 @@ __global__ void __launch_bounds__(kChase8Threads)
     }
     const int g = tid >> 3, q = tid & 7;
     const unsigned gmask = 0xffu << (lane & 24);
+    // Sweeps shorter than 12 steps (k >= S) need only FOUR groups to keep the one-sweep-per-three-ticks rate (4 x lag = 12
+    // ticks per round): they run on the groups of warp 0, and warp 1 sits the second half of the ticks out (23 % fewer
+    // instructions; the kernel is throughput-bound on issue slots and the shared-memory pipe together).
+    const int S = ((n > 97 ? n - 97 : 0) + 7) / 8 * 8;
     int k = g, j = 0;
-    bool active = g <= n - 3;
+    bool active = g <= n - 3 && (g < 4 || g < S);
     if (q == 0) prog[g] = k | (j << 16) | (active ? 1 << 24 : 0);
     int par = 0;
     while (__syncthreads_or(active)) {  // the barrier also orders last tick's stores and progress entries
         bool ready = false;
         if (active) {
-            const int pg = (g + kChase8Groups - 1) % kChase8Groups;
+            const int pg = (k > S) ? ((g + 3) & 3) : ((g + kChase8Groups - 1) % kChase8Groups);  // the group that runs sweep k - 1
             const int pv = prog[kChase8Groups * par + pg];
             const int kp = pv & 0xffff, jp = (pv >> 16) & 0xff, ap = pv >> 24;
             ready = (k == 0) || (ap == 0) || (kp > k - 1) || (kp == k - 1 && jp >= j + kChase8Lag);
@@ -93,7 +97,7 @@ __global__ void __launch_bounds__(kChase8Threads)
         // Every lane runs the step body, converged: groups that are not ready work on row 0 and store nothing.  (With
         // the body under `if (ready)` the eight-lane exchange became a sub-warp shuffle in divergent code, which
         // the compiler lowers to a WARPSYNC.COLLECTIVE loop.)
-        {
+        if (__any_sync(0xffffffffu, active)) {  // warp-uniform
             const int r0 = ready ? k + 1 + 8 * j : 0;
             const int xj = (j == 0) ? 1 : 8;  // jj of x_0: column r0-1 (first step) or r0-8
             double* Lr = L + (size_t)r0 * kChase8W;
@@ -181,9 +185,9 @@ __global__ void __launch_bounds__(kChase8Threads)
         if (ready) {
             ++j;
             if (k + 1 + 8 * j > n - 2) {
-                k += kChase8Groups;
+                k += (k >= S) ? 4 : kChase8Groups;  // (k < S: k + 8 = S + g when it crosses S)
                 j = 0;
-                if (k > n - 3) active = false;
+                if (k > n - 3 || (k >= S && g >= 4)) active = false;
             }
         }
         if (q == 0) {  // every tick, ready or not: the other buffer is one tick old

@@ -90,6 +90,7 @@ struct ShapeClass {
     int64_t refine_items_off;     // byte offset of the slot -> item table
     int refine_counter;           // index of this class's slot counter
     int refine_B;                 // CTAs per cluster of the re-solve (0: one-CTA kernel)
+    bool refine_shared = false;   // re-solve entry point that leaves room for bisection CTAs on its SMs (n <= 256, large classes)
     mutable int refine_launch_slots = 0;  // clusters per launch: refine_slots capped by what is resident at once (first execution)
     int refine_kmax;              // largest contraction length of the class
     int refine_xs_cap;            // doubles of shared memory for a CTA's share of X
@@ -430,7 +431,11 @@ static int plan_layout(vsp_plan* p, int32_t count, const int32_t* rows, const in
                 // n > 256: a step sweeps the CTA's share of X in L2 three times, so the step time follows the share: sixteen
                 // CTAs (non-portable cluster size, one GPC each: 8 resident clusters; n = 768: 14.8 ms per matrix) while the
                 // flagged matrices of a random-init class (~4 %) fit one round, else eight (22 ms, but 25 % fewer SM-ms)
-                int B = c.n <= 256 ? 3 : (c.count <= 200 ? kRcMaxCluster : 8);
+                // n <= 256, small class (a single checkpoint, the short chunks at the ends of a host sweep): the bisection
+                // kernel is over in a fraction of a millisecond, so the re-solve of a flagged matrix IS the latency of the
+                // call: all registers and four CTAs (1.5 instead of 2.2 ms per matrix)
+                c.refine_shared = c.n <= 256 && c.count > 1024;
+                int B = c.n <= 256 ? (c.refine_shared ? 3 : 4) : (c.count <= 200 ? kRcMaxCluster : 8);
                 if (const char* e = std::getenv("VSP_REFINE_B")) B = std::max(1, std::min(kRcMaxCluster, std::atoi(e)));  // experiments
                 for (int s = c.begin; s < c.begin + c.count; ++s) {
                     kmax = std::max(kmax, p->items[s].kdim);
@@ -707,7 +712,7 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
             VSP_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
             if (c.refine_B > 0) {
                 const int B = c.refine_B, Kpad = round_up(c.refine_kmax, 4), nloc = (c.n + B - 1) / B;
-                const size_t smem_d = std::max(refine_cluster_fixed_doubles(c.npad, Kpad, nloc, c.n <= 256) + (size_t)c.refine_xs_cap,
+                const size_t smem_d = std::max(refine_cluster_fixed_doubles(c.npad, Kpad, nloc, c.refine_shared) + (size_t)c.refine_xs_cap,
                                                refine_cluster_tail_doubles(c.npad));
                 const size_t csmem = smem_d * sizeof(double);
                 cudaLaunchConfig_t cfg = {};
@@ -722,7 +727,7 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
                 attr[0].val.clusterDim.z = 1;
                 cfg.attrs = attr;
                 cfg.numAttrs = 1;
-                const bool shared = c.n <= 256;  // runs beside the bisection kernel: capped registers, maximum carve-out
+                const bool shared = c.refine_shared;  // runs beside the bisection kernel: capped registers, maximum carve-out
 #define VSP_RC_LAUNCH(KERNEL)                                                                                             \
     {                                                                                                                   \
         VSP_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(csmem, 48 * 1024))); \

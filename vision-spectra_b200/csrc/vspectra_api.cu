@@ -109,8 +109,6 @@ int validate(int32_t count, const int32_t* rows, const int32_t* cols, const int6
 
 }  // namespace
 
-constexpr int kMaxGramGroups = 8;
-
 struct vsp_plan {
     int count = 0;
     int dtype = VSP_F32;
@@ -131,7 +129,6 @@ struct vsp_plan {
     // the re-solve of ill-conditioned items runs beside the bisection kernel on a forked stream
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    cudaEvent_t ev_slice[kMaxGramGroups] = {};  // stage 1: slices of the later (n, Kp) groups, on the side stream
 };
 
 namespace {
@@ -173,35 +170,17 @@ int make_plane_map(CUtensorMap* map, void* base, const I8Class& c, int box_rows)
     return VSP_OK;
 }
 
-// stage 1 on the tensor cores for every (n, Kp) group of this shape class.  The slice kernel is ALU-bound (digit
-// extraction) and the MMA kernel leaves the ALUs idle (one CTA of 192 threads per SM: its seven level accumulators
-// take 448 of the 512 TMEM columns), so the slices of the groups after the first run on the side stream, beside the
-// first group's MMAs, and each later MMA launch waits for its own slices only.
+// stage 1 on the tensor cores for every (n, Kp) group of this shape class: slices, then the persistent MMA kernel.
+// (Running a later group's slices on a side stream beside an earlier group's MMAs was measured and gains nothing:
+// the MMA CTA fills its SM)
 int launch_gram_i8(const vsp_plan* p, const ShapeClass& c, double* ws, unsigned char* wsb, int* inexact, cudaStream_t st) {
-    static const bool serial = std::getenv("VSP_GRAM_SERIAL") != nullptr;  // experiments: no overlap
-    std::vector<const I8Class*> groups;
-    for (const I8Class& g : p->i8classes)
-        if (g.n == c.n) groups.push_back(&g);
-    const int ng = (int)groups.size();
-    const bool overlap = !serial && ng > 1 && ng <= kMaxGramGroups;
-    auto slice = [&](const I8Class& g, cudaStream_t sst) -> int {
+    for (const I8Class& g : p->i8classes) {
+        if (g.n != c.n) continue;
         dim3 sgrid(g.count, (g.n + 31) / 32);
-        slice_i8_kernel<<<sgrid, 256, 0, sst>>>(p->d_items, g, wsb, inexact);
+        slice_i8_kernel<<<sgrid, 256, 0, st>>>(p->d_items, g, wsb, inexact);
         g_launches++;
-        t_timer.tick("slice_i8", sst);
-        return cuda_ok(cudaGetLastError(), "slice_i8_kernel") ? VSP_OK : VSP_E_CUDA;
-    };
-    if (ng > 0) {
-        const int rc = slice(*groups[0], st);
-        if (rc != VSP_OK) return rc;
-    }
-    for (int gi = 0; gi < ng; ++gi) {
-        const I8Class& g = *groups[gi];
-        if (overlap && gi > 0) VSP_CUDA(cudaStreamWaitEvent(st, p->ev_slice[gi], 0));
-        // the next group's slices become runnable together with this group's MMAs and are enqueued after them, so the
-        // MMA CTAs are placed first and the slice CTAs fill the room they leave (enqueued earlier, the slices only
-        // shared the ALUs with the previous slices and were done before any MMA ran: measured, no gain)
-        if (overlap && gi + 1 < ng) VSP_CUDA(cudaEventRecord(p->ev_fork, st));
+        t_timer.tick("slice_i8", st);
+        if (!cuda_ok(cudaGetLastError(), "slice_i8_kernel")) return VSP_E_CUDA;
         CUtensorMap tmA, tmB;
         int rc = make_plane_map(&tmA, wsb + g.slice_off, g, kI8TileM);
         if (rc == VSP_OK) rc = make_plane_map(&tmB, wsb + g.slice_off, g, kI8TileN);
@@ -209,22 +188,12 @@ int launch_gram_i8(const vsp_plan* p, const ShapeClass& c, double* ws, unsigned 
         if (!cuda_ok(cudaFuncSetAttribute(gram_i8_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kI8SmemBytes),
                      "cudaFuncSetAttribute(gram_i8_mma_kernel)"))
             return VSP_E_CUDA;
-        if (overlap) {  // both kernels on the maximum carve-out, or the slice CTAs do not fit beside an MMA CTA
-            VSP_CUDA(cudaFuncSetAttribute(gram_i8_mma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            VSP_CUDA(cudaFuncSetAttribute(slice_i8_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        }
         static const int mma_grid = std::getenv("VSP_GRAM_GRID") ? std::atoi(std::getenv("VSP_GRAM_GRID")) : 0;  // experiments
         const int mgrid = std::min(g.mtiles * g.count, mma_grid > 0 ? mma_grid : p->sm_count);  // persistent: a CTA per SM
         gram_i8_mma_kernel<<<mgrid, kI8Threads, kI8SmemBytes, st>>>(p->d_items, g, wsb, ws, tmA, tmB);
         g_launches++;
         t_timer.tick("gram_i8_mma", st);
         if (!cuda_ok(cudaGetLastError(), "gram_i8_mma_kernel")) return VSP_E_CUDA;
-        if (gi + 1 < ng) {
-            if (overlap) VSP_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
-            rc = slice(*groups[gi + 1], overlap ? p->side : st);
-            if (rc != VSP_OK) return rc;
-            if (overlap) VSP_CUDA(cudaEventRecord(p->ev_slice[gi + 1], p->side));
-        }
     }
     return VSP_OK;
 }
@@ -490,11 +459,6 @@ int vsp_plan_create(int32_t count, const int32_t* rows, const int32_t* cols, con
             vsp_plan_destroy(p);
             return VSP_E_CUDA;
         }
-        for (cudaEvent_t& e : p->ev_slice)
-            if (!cuda_ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate")) {
-                vsp_plan_destroy(p);
-                return VSP_E_CUDA;
-            }
     }
     *out_plan = p;
     return VSP_OK;
@@ -514,8 +478,6 @@ void vsp_plan_destroy(vsp_plan* plan) {
     if (plan->side) cudaStreamDestroy(plan->side);
     if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
     if (plan->ev_join) cudaEventDestroy(plan->ev_join);
-    for (cudaEvent_t e : plan->ev_slice)
-        if (e) cudaEventDestroy(e);
     delete plan;
 }
 

@@ -65,42 +65,56 @@ __device__ __forceinline__ int f32_exp_field(unsigned bits) {
     return ex ? ex : 1;  // zero / denormal: exponent field 1, no implicit bit
 }
 
-// six balanced base-128 digits of x relative to row exponent E, most significant first
-// Returns the SQUARE of the rounding residual in units of the row's quantum 2^(E-167) (0 for elements within 2^17 of
-// the row maximum, at most 1/4 otherwise).  A Gram row whose residuals add up to more than one quantum (sum of squares
-// > 1: a dozen rounded elements -- outlier columns, a single huge entry; a random-init row has none or one) marks
-// the matrix "rounded": its Gram matrix is then only accurate to ~K 2^-42 ||G|| and the eigensolve hands it to
-// the FP64 re-solve earlier (kRefineRatioInexact, bisect_metrics.cuh).
-__device__ __forceinline__ float f32_digits(unsigned bits, int E, signed char (&dg)[kDigits]) {
-    const int exf = (bits >> 23) & 0xff;
-    long long man = bits & 0x7fffff;
-    if (exf) man |= 0x800000;
-    const int sh = 17 - (E - (exf ? exf : 1));
-    long long q;
-    float res2 = 0.f;
-    if (sh >= 0) {
-        q = man << sh;
-    } else {
-        const int r = -sh;
-        q = (r > 40) ? 0 : ((man + (1LL << (r - 1))) >> r);
-        const float res = (r > 40) ? 0.f : (float)(man - (q << r)) * exp2f((float)-r);  // |res| <= 1/2 quantum
-        res2 = res * res;
-    }
-    if (bits >> 31) q = -q;
-    // balanced digits s_t in [-64, 63] (s_0 up to 64) of q = ordinary base-128 digits of q + 64 (128^5 + ... + 1), minus 64:
-    // no carry chain, six shift-and-mask steps
+// Six balanced base-128 digits (most significant first) of four consecutive elements of a Gram row, relative to the
+// row exponent E, packed as the four bytes of one word per digit plane.
+//   q = round(x 2^(167-E)), |q| < 2^41 (elements more than 2^17 below the row maximum lose their low bits here);
+//   balanced digits s_t in [-64, 63] (s_0 up to 64) of q = ordinary base-128 digits of qb = q + 64 (128^5 + ... + 1),
+//   minus 64: no carry chain.
+// One FMA does the scaling, the rounding (to nearest even) and the bias: t = x 2^(167-E) + (1.5 2^52 + bias) has qb
+// in its low mantissa bits (0 <= qb < 129 128^5 < 2^43), so the digits are 7-bit fields of the two words of t --
+// 32-bit shifts and masks that land each field directly in its byte; the "- 64" is applied per packed word (a 7-bit
+// field d minus 64 as a two's-complement byte is d with bit 6 flipped and bit 7 = not bit 6).  About 25 instructions
+// per element; the 64-bit integer version this replaces took about 70 and made the slice kernel ALU-bound.
+// res2 accumulates the SQUARES of the rounding residuals in units of the row's quantum 2^(E-167) (0 for elements
+// within 2^17 of the row maximum, at most 1/4 otherwise).  A Gram row whose residuals add up to more than one quantum
+// (a dozen rounded elements -- outlier columns, a single huge entry; a random-init row has none or one) marks the
+// matrix "rounded": its Gram matrix is then only accurate to ~K 2^-42 ||G|| and the eigensolve hands it to the FP64
+// re-solve earlier (kRefineRatioInexact, bisect_metrics.cuh).  Elements beyond the row end are passed as 0.0f
+// (digits 0, no residual).
+__device__ __forceinline__ void f32_digits4(const float (&xv)[4], int E, unsigned (&pk)[kDigits], double& res2) {
     constexpr long long kBias = 64LL * ((1LL << 42) - 1) / 127;
-    const unsigned long long qb = (unsigned long long)(q + kBias);  // 0 <= qb < 129 * 128^5
-    dg[0] = (signed char)((int)(qb >> 35) - 64);
+    const double magic = 6755399441055744.0 + (double)kBias;  // 1.5 * 2^52 + bias (exact)
+    const double scale = __hiloint2double((1190 - E) << 20, 0);  // 2^(167 - E), E = 1..254 (255: the row is NaN/Inf)
 #pragma unroll
-    for (int t = 1; t < kDigits; ++t) dg[t] = (signed char)((int)((qb >> (7 * (kDigits - 1 - t))) & 127) - 64);
-    return res2;
+    for (int t = 0; t < kDigits; ++t) pk[t] = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const double xd = (double)xv[u];
+        const double tt = fma(xd, scale, magic);
+        const double q = tt - magic;                 // exact: the rounded integer
+        const double res = fma(xd, scale, -q);       // exact: |res| <= 1/2
+        res2 = fma(res, res, res2);
+        const unsigned lo = (unsigned)__double2loint(tt);
+        const unsigned hi = (unsigned)__double2hiint(tt) - 0x43380000u;  // qb >> 32
+        const int sb = 8 * u;
+        // planes 5..2: bits 0-6, 7-13, 14-20, 21-27 of lo, moved straight to byte u
+        pk[5] |= (lo << sb) & (0x7fu << sb);
+        pk[4] |= (sb >= 7 ? (lo << (sb - 7)) : (lo >> (7 - sb))) & (0x7fu << sb);
+        pk[3] |= (sb >= 14 ? (lo << (sb - 14)) : (lo >> (14 - sb))) & (0x7fu << sb);
+        pk[2] |= (sb >= 21 ? (lo << (sb - 21)) : (lo >> (21 - sb))) & (0x7fu << sb);
+        // plane 1: bits 28-34 (four bits of lo, three of hi)
+        pk[1] |= (__funnelshift_r(lo, hi, 28) & 0x7fu) << sb;
+        // plane 0: qb >> 35 in 0..128: plain subtraction
+        pk[0] |= (((hi >> 3) - 64u) & 0xffu) << sb;
+    }
+#pragma unroll
+    for (int t = 1; t < kDigits; ++t) pk[t] = (pk[t] ^ 0x40404040u) | ((~pk[t] & 0x40404040u) << 1);
 }
 
 // One CTA per (item, block of 32 Gram rows).  256 threads.
 //   trans == 0 : Gram row i = row i of W (contiguous K): warp per row.
 //   trans == 1 : Gram row i = column i of W: lanes on columns, digits transposed through smem.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
     slice_i8_kernel(const ItemDesc* __restrict__ items, I8Class cls, unsigned char* __restrict__ wsb, int* __restrict__ inexact) {
     const ItemDesc it = items[cls.begin + blockIdx.x];
     const int n = it.n, K = it.kdim, kp = cls.kp;
@@ -121,20 +135,81 @@ __global__ void __launch_bounds__(256)
             const int i = i0 + r;
             if (i >= n) continue;  // warp-uniform
             const float* row = W + (int64_t)i * ld;
+            if (K <= 256 && (reinterpret_cast<uintptr_t>(row) & 15) == 0 && (K & 3) == 0) {
+                // short aligned row: ONE pass, the row lives in two float4 per lane between its load and the digit stores
+                // (the two-pass form below reads every row twice with a shuffle reduction in between: latency-bound)
+                float xa[4] = {0.f, 0.f, 0.f, 0.f}, xb[4] = {0.f, 0.f, 0.f, 0.f};
+                const int ka = 4 * lane, kb = 128 + 4 * lane;
+                if (ka < K) {
+                    const float4 f = *reinterpret_cast<const float4*>(row + ka);
+                    xa[0] = f.x, xa[1] = f.y, xa[2] = f.z, xa[3] = f.w;
+                }
+                if (kb < K) {
+                    const float4 f = *reinterpret_cast<const float4*>(row + kb);
+                    xb[0] = f.x, xb[1] = f.y, xb[2] = f.z, xb[3] = f.w;
+                }
+                int e = 1;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    e = max(e, (int)((__float_as_uint(xa[u]) >> 23) & 0xff));
+                    e = max(e, (int)((__float_as_uint(xb[u]) >> 23) & 0xff));
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) e = max(e, __shfl_xor_sync(0xffffffffu, e, o));
+                if (lane == 0) Eout[i] = e;
+                double res2 = 0.0;
+                unsigned pk[kDigits];
+                if (ka < kp) {
+                    f32_digits4(xa, e, pk, res2);
+#pragma unroll
+                    for (int t = 0; t < kDigits; ++t) *reinterpret_cast<unsigned*>(planes + ((int64_t)t * n + i) * kp + ka) = pk[t];
+                }
+                if (kb < kp) {
+                    f32_digits4(xb, e, pk, res2);
+#pragma unroll
+                    for (int t = 0; t < kDigits; ++t) *reinterpret_cast<unsigned*>(planes + ((int64_t)t * n + i) * kp + kb) = pk[t];
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) res2 += __shfl_xor_sync(0xffffffffu, res2, o);
+                any_rounded |= res2 > 1.0;
+                continue;
+            }
             int e = 1;
-            for (int k = lane; k < K; k += 32) {
-                const unsigned b = __float_as_uint(row[k]);
-                const int ex = (b >> 23) & 0xff;
-                e = max(e, ex ? ex : 1);
+            const bool vec = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+            if (vec) {  // 128-bit loads, four in flight per lane
+                const int K4 = K >> 2;
+                const float4* row4 = reinterpret_cast<const float4*>(row);
+                int k4 = lane;
+                for (; k4 + 96 < K4; k4 += 128) {
+                    float4 f[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) f[u] = row4[k4 + 32 * u];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        e = max(e, (int)((__float_as_uint(f[u].x) >> 23) & 0xff));
+                        e = max(e, (int)((__float_as_uint(f[u].y) >> 23) & 0xff));
+                        e = max(e, (int)((__float_as_uint(f[u].z) >> 23) & 0xff));
+                        e = max(e, (int)((__float_as_uint(f[u].w) >> 23) & 0xff));
+                    }
+                }
+                for (; k4 < K4; k4 += 32) {
+                    const float4 f = row4[k4];
+                    e = max(e, (int)((__float_as_uint(f.x) >> 23) & 0xff));
+                    e = max(e, (int)((__float_as_uint(f.y) >> 23) & 0xff));
+                    e = max(e, (int)((__float_as_uint(f.z) >> 23) & 0xff));
+                    e = max(e, (int)((__float_as_uint(f.w) >> 23) & 0xff));
+                }
+                for (int k = (K4 << 2) + lane; k < K; k += 32) e = max(e, (int)((__float_as_uint(row[k]) >> 23) & 0xff));
+            } else {
+                for (int k = lane; k < K; k += 32) e = max(e, (int)((__float_as_uint(row[k]) >> 23) & 0xff));
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) e = max(e, __shfl_xor_sync(0xffffffffu, e, o));
             if (lane == 0) Eout[i] = e;
-            float res2 = 0.f;
+            double res2 = 0.0;
             // four consecutive k per lane: one 128-bit load (when the row is 16-byte aligned), one 32-bit store per plane
-            const bool vec = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
             for (int k = 4 * lane; k < kp; k += 128) {
-                unsigned pk[kDigits] = {0, 0, 0, 0, 0, 0};
+                unsigned pk[kDigits];
                 float xv[4] = {0.f, 0.f, 0.f, 0.f};
                 if (vec && k + 3 < K) {
                     const float4 f = *reinterpret_cast<const float4*>(row + k);
@@ -144,38 +219,37 @@ __global__ void __launch_bounds__(256)
                     for (int u = 0; u < 4; ++u)
                         if (k + u < K) xv[u] = row[k + u];
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    signed char dg[kDigits] = {0, 0, 0, 0, 0, 0};
-                    if (k + u < K) res2 += f32_digits(__float_as_uint(xv[u]), e, dg);
-#pragma unroll
-                    for (int t = 0; t < kDigits; ++t) pk[t] |= (unsigned)(unsigned char)dg[t] << (8 * u);
-                }
+                f32_digits4(xv, e, pk, res2);
 #pragma unroll
                 for (int t = 0; t < kDigits; ++t)
                     *reinterpret_cast<unsigned*>(planes + ((int64_t)t * n + i) * kp + k) = pk[t];
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) res2 += __shfl_xor_sync(0xffffffffu, res2, o);
-            any_rounded |= res2 > 1.f;
+            any_rounded |= res2 > 1.0;
         }
     } else {
         // column maxima: warp w scans rows k = w, w+8, ...; lanes on the 32 columns of this block
         const int i = i0 + lane;
         int e = 1;
-        if (i < n)
-            for (int k = warp; k < K; k += 8) {
-                const unsigned b = __float_as_uint(W[(int64_t)k * ld + i]);
-                const int ex = (b >> 23) & 0xff;
-                e = max(e, ex ? ex : 1);
+        if (i < n) {
+            int k = warp;
+            for (; k + 56 < K; k += 64) {  // eight loads in flight per lane
+                float f[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) f[u] = W[(int64_t)(k + 8 * u) * ld + i];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) e = max(e, (int)((__float_as_uint(f[u]) >> 23) & 0xff));
             }
+            for (; k < K; k += 8) e = max(e, (int)((__float_as_uint(W[(int64_t)k * ld + i]) >> 23) & 0xff));
+        }
         if (tid < 32) sE[tid] = 1;
         __syncthreads();
         atomicMax(&sE[lane], e);
         __syncthreads();
         if (tid < 32 && i0 + tid < n) Eout[i0 + tid] = sE[tid];
         const int Ei = sE[lane];
-        float res2 = 0.f;  // this thread's share of Gram row i0 + lane
+        double res2 = 0.0;  // this thread's share of Gram row i0 + lane
         // digits staged as 32-bit words (four consecutive k of one Gram row), row pitch 17 words: lanes (= Gram rows) fall
         // into different banks (the byte-granular staging at an 80-byte pitch ran at 4-way conflicts: ncu r01)
         unsigned(*sw)[32][17] = reinterpret_cast<unsigned(*)[32][17]>(&sdig[0][0][0]);
@@ -183,20 +257,14 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int kw = warp + 8 * j;  // word index inside the 64-byte chunk: k = k0 + 4 kw .. + 3
-                unsigned pk[kDigits] = {0, 0, 0, 0, 0, 0};
+                unsigned pk[kDigits];
                 float xv[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int k = k0 + 4 * kw + u;
                     xv[u] = (k < K && i < n) ? W[(int64_t)k * ld + i] : 0.f;
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    signed char dg[kDigits] = {0, 0, 0, 0, 0, 0};
-                    if (k0 + 4 * kw + u < K && i < n) res2 += f32_digits(__float_as_uint(xv[u]), Ei, dg);
-#pragma unroll
-                    for (int t = 0; t < kDigits; ++t) pk[t] |= (unsigned)(unsigned char)dg[t] << (8 * u);
-                }
+                f32_digits4(xv, Ei, pk, res2);
 #pragma unroll
                 for (int t = 0; t < kDigits; ++t) sw[t][lane][kw] = pk[t];
             }
@@ -210,7 +278,7 @@ __global__ void __launch_bounds__(256)
         }
         // per Gram row: the eight warps' shares meet in shared memory (the digit staging buffer is free now)
         float* sres = reinterpret_cast<float*>(&sdig[0][0][0]);  // [8][32]
-        sres[warp * 32 + lane] = res2;
+        sres[warp * 32 + lane] = (float)res2;
         __syncthreads();
         if (warp == 0) {
             float tot = 0.f;

@@ -403,7 +403,7 @@ static int plan_layout(vsp_plan* p, int32_t count, const int32_t* rows, const in
                 // n <= 256, small class (a single checkpoint, the short chunks at the ends of a host sweep): the bisection
                 // kernel is over in a fraction of a millisecond, so the re-solve of a flagged matrix IS the latency of the
                 // call: all registers and four CTAs (1.5 instead of 2.2 ms per matrix)
-                c.refine_shared = c.n <= 256 && c.count > 1024;
+                c.refine_shared = c.n <= 256 && c.count > 2048;  // (1 116 matrices: bisection 0.8 ms against 1.9 ms of shared re-solve)
                 int B = c.n <= 256 ? (c.refine_shared ? 3 : 4) : (c.count <= 200 ? kRcMaxCluster : 8);
                 if (const char* e = std::getenv("VSP_REFINE_B")) B = std::max(1, std::min(kRcMaxCluster, std::atoi(e)));  // experiments
                 for (int s = c.begin; s < c.begin + c.count; ++s) {

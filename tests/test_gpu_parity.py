@@ -375,6 +375,25 @@ def test_resolve_pool_serves_every_flagged_matrix(engine):
             _check_record(f"pool{i}", w, m, s, r, orc.get_spectral_metrics(w), orc.integer_outputs(w), ref_sv)
 
 
+def test_resolve_of_large_orders_on_wide_clusters(engine):
+    """Ill-conditioned matrices above order 256 take the 16-CTA (or 8-CTA) cluster re-solve with its share of X in L2:
+    the one-sweep step (K <= 768: right update + next left reflector with the column in registers) and the
+    three-sweep step (K > 768) must both land inside the element-wise singular-value gate."""
+    rng = np.random.default_rng(2024)
+    host = []
+    for n, K in ((300, 300), (300, 1100), (768, 768), (520, 640)):
+        u = np.linalg.qr(rng.standard_normal((K, n)))[0]
+        v = np.linalg.qr(rng.standard_normal((n, n)))[0]
+        s = np.logspace(0, -6.5, n)
+        host.append((u * s) @ v.T)  # float64, K x n
+    host.append(trunc_normal(rng, (768, 768)))  # a well-conditioned one beside them
+    metrics, svs, rec = engine.analyze([torch.from_numpy(w).cuda() for w in host])
+    for i, (w, m, s, r) in enumerate(zip(host, metrics, svs, rec)):
+        if i < 4:
+            assert int(r["status"]) & 96 == 96, (i, int(r["status"]))
+        _check_record(f"wide{i}", w, m, s, r, orc.get_spectral_metrics(w), orc.integer_outputs(w), orc.singular_values(w))
+
+
 def test_workspace_bound_covers_every_plan(engine):
     """vsp_workspace_bytes (shape-only bound of the one-shot entry) is laid out by the same code as a plan: it must
     cover classes whose items share n but differ wildly in K (the re-solve pool is sized by the largest K*n)."""

@@ -56,8 +56,25 @@ struct I8Class {
     int64_t slice_off;  // byte offset of the [count][6][n][kp] digit planes in the workspace
     int64_t exp_off;    // byte offset of the [count][n] int32 row exponents
     int mtiles;                          // 128-row tiles
-    unsigned char nt_count[kI8MaxTiles];  // 64-column tiles of the lower triangle per 128-row tile
+    unsigned char nt_count[kI8MaxTiles];  // 64-column tiles computed by the 128-row tile (see xt)
+    // When the last 128-row tile has at most 64 rows (n = 192: rows 128..191), its off-diagonal blocks are the transposes
+    // of the blocks (earlier row tile) x (column tile xt = columns 128 mtl .. + 63), which fill their MMAs completely:
+    // every earlier row tile computes that one extra column tile and stores it transposed, the last row tile only
+    // its diagonal block (n = 192: 3 + 1 tiles instead of 2 + 3).  xt < 0: plain lower-triangle enumeration.
+    int xt;
 };
+
+// column tile computed as tile `ti` of row tile `mt`, and whether it is stored transposed
+__host__ __device__ inline int i8_tile_nt(const I8Class& c, int mt, int ti, bool& transposed) {
+    transposed = false;
+    if (c.xt < 0) return ti;
+    if (mt == c.mtiles - 1) return c.xt;  // the last row tile: its diagonal block only
+    if (ti == 2 * mt + 2) {
+        transposed = true;
+        return c.xt;
+    }
+    return ti;
+}
 
 // ---------------------------------------------------------------------------------- slicing
 __device__ __forceinline__ int f32_exp_field(unsigned bits) {
@@ -421,7 +438,9 @@ __global__ void __launch_bounds__(kI8Threads, 1)
                 const int n = cls.n;
                 const int ntiles = cls.nt_count[mt];
                 const int rowA = item * kDigits * n + mt * kI8TileM;  // + t*n per digit plane
-                for (int nt = 0; nt < ntiles; ++nt) {
+                for (int ti = 0; ti < ntiles; ++ti) {
+                    bool tr_unused;
+                    const int nt = i8_tile_nt(cls, mt, ti, tr_unused);
                     const int rowB = item * kDigits * n + nt * kI8TileN;
                     for (int c = 0; c < nchunks; ++c, ++g) {
                         const int s = g % kI8Stages;
@@ -542,7 +561,9 @@ __global__ void __launch_bounds__(kI8Threads, 1)
             for (int k = 0; k < 4; ++k) Er[k] = (row0 + 8 * k < n) ? E[row0 + 8 * k] : 1;
             const bool fast = layout == kGramTiled && foff == 0;  // n is a multiple of 8: a warp's (h, v, m) block is one tile
             for (int ti = 0; ti < ntiles; ++ti, ++tile) {
-                const int col0 = ti * kI8TileN + 32 * ch + lc;  // columns of this thread: col0 + 8 m + e
+                bool transposed;
+                const int nt = i8_tile_nt(cls, mt, ti, transposed);
+                const int col0 = nt * kI8TileN + 32 * ch + lc;  // columns of this thread: col0 + 8 m + e
                 int Ec[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) Ec[k] = (col0 + 8 * (k >> 1) + (k & 1) < n) ? E[col0 + 8 * (k >> 1) + (k & 1)] : 1;
@@ -583,7 +604,7 @@ __global__ void __launch_bounds__(kI8Threads, 1)
                         const int I = (mt * kI8TileM + 32 * q + 16 * h + 8 * v) >> 3;  // tile row (warp-uniform)
 #pragma unroll
                         for (int m = 0; m < 4; ++m) {
-                            const int J = (ti * kI8TileN + 32 * ch + 8 * m) >> 3;  // tile column (warp-uniform)
+                            const int J = (nt * kI8TileN + 32 * ch + 8 * m) >> 3;  // tile column (warp-uniform)
                             double g[2];
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
@@ -592,7 +613,13 @@ __global__ void __launch_bounds__(kI8Threads, 1)
                                 g[e] = (Ei == 255 || Ej == 255) ? __longlong_as_double(0x7ff8000000000000LL)  // NaN/Inf in the input row
                                                                 : acc[16 * h + 4 * m + 2 * v + e] * __hiloint2double(be << 20, 0);
                             }
-                            if (fast) {
+                            if (fast && transposed) {
+                                // block above the diagonal (J > I): stored as its transpose, tile (J, I)
+                                if (8 * I >= n || 8 * J >= n) continue;  // warp-uniform
+                                double* dst = G + tile_off(J, I) + (lc << 3) + lr;
+                                dst[0] = g[0];
+                                dst[8] = g[1];
+                            } else if (fast) {
                                 if (8 * I >= n || J > I) continue;  // warp-uniform
                                 if (J == I) {
                                     // diagonal tile: both triangles.  Position (lr, lc + e) above the diagonal takes the value
@@ -609,17 +636,18 @@ __global__ void __launch_bounds__(kI8Threads, 1)
                             } else if (R < n) {
 #pragma unroll
                                 for (int e = 0; e < 2; ++e) {
-                                    const int C = ti * kI8TileN + 32 * ch + 8 * m + lc + e;
-                                    if (C > R) continue;
+                                    const int C = nt * kI8TileN + 32 * ch + 8 * m + lc + e;
+                                    const int gi = transposed ? C : R, gj = transposed ? R : C;  // stored position (gi, gj), gj <= gi
+                                    if (gj > gi || gi >= n) continue;
                                     if (layout == kGramTiled) {
-                                        const int fi = R + foff, fj = C + foff;
+                                        const int fi = gi + foff, fj = gj + foff;
                                         G[tile_off(fi >> 3, fj >> 3) + ((fi & 7) << 3) + (fj & 7)] = g[e];
                                         if ((fj >> 3) == (fi >> 3)) G[tile_off(fi >> 3, fi >> 3) + ((fj & 7) << 3) + (fi & 7)] = g[e];
                                     } else if (layout == kGramFull) {
-                                        G[(int64_t)R * n + C] = g[e];
-                                        G[(int64_t)C * n + R] = g[e];
+                                        G[(int64_t)gi * n + gj] = g[e];
+                                        G[(int64_t)gj * n + gi] = g[e];
                                     } else {
-                                        G[poff(R) + C] = g[e];
+                                        G[poff(gi) + gj] = g[e];
                                     }
                                 }
                             }

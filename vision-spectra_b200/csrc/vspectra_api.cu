@@ -359,9 +359,13 @@ static int plan_layout(vsp_plan* p, int32_t count, const int32_t* rows, const in
                 c.begin = s;
                 c.count = 0;
                 c.mtiles = (it.n + kI8TileM - 1) / kI8TileM;  // <= 32 for n <= VSP_MAX_N
+                const int mtl = c.mtiles - 1, tail_rows = it.n - mtl * kI8TileM;
+                static const bool no_xt = std::getenv("VSP_GRAM_NO_XT") != nullptr;  // experiments
+                c.xt = (!no_xt && mtl >= 1 && tail_rows <= kI8TileN) ? 2 * mtl : -1;  // gram_i8.cuh: I8Class::xt
                 for (int mt = 0; mt < c.mtiles; ++mt) {
                     const int last_col = std::min(it.n - 1, mt * kI8TileM + kI8TileM - 1);
                     c.nt_count[mt] = (unsigned char)(last_col / kI8TileN + 1);
+                    if (c.xt >= 0) c.nt_count[mt] = (unsigned char)(mt == mtl ? 1 : 2 * mt + 3);
                 }
                 p->i8classes.push_back(c);
             }

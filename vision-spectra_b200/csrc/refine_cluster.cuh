@@ -427,6 +427,15 @@ __global__ void __launch_bounds__(kRcThreads)
                           double* __restrict__ dist_out) {
     refine_cluster_body<TIn, true, kRcRplWide, false>(items, gate, pool, npad, Kpad, nloc_max, xs_cap, opts, sv_out, records, dist_out);
 }
+// n <= 256, small classes: all registers like the entry point above, but the one-sweep step sized for K <= 256 (the
+// K <= 768 instantiation walks 24 register slots per lane of which a 192-row column fills six)
+template <typename TIn>
+__global__ void __launch_bounds__(kRcThreads)
+    refine_cluster_small_kernel(const ItemDesc* __restrict__ items, RefineGate gate, RefinePool pool, int npad, int Kpad,
+                                int nloc_max, int xs_cap, vsp_opts opts, double* __restrict__ sv_out,
+                                vsp_record* __restrict__ records, double* __restrict__ dist_out) {
+    refine_cluster_body<TIn, false, 8, false>(items, gate, pool, npad, Kpad, nloc_max, xs_cap, opts, sv_out, records, dist_out);
+}
 template <typename TIn>
 __global__ void __maxnreg__(64)
     refine_cluster_shared_kernel(const ItemDesc* __restrict__ items, RefineGate gate, RefinePool pool, int npad, int Kpad,

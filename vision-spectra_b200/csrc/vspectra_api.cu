@@ -712,11 +712,14 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
         VSP_CUDA(cudaLaunchKernelEx(&cfg, KERNEL, (const ItemDesc*)p->d_items, gate, pool, c.npad, Kpad, nloc, c.refine_xs_cap, \
                                     p->opts, d_sv, d_records, d_dist));                                                 \
     }
+                const bool small = !shared && c.n <= 256;
                 if (p->dtype == VSP_F32) {
                     if (shared) VSP_RC_LAUNCH(refine_cluster_shared_kernel<float>)
+                    else if (small) VSP_RC_LAUNCH(refine_cluster_small_kernel<float>)
                     else VSP_RC_LAUNCH(refine_cluster_kernel<float>)
                 } else {
                     if (shared) VSP_RC_LAUNCH(refine_cluster_shared_kernel<double>)
+                    else if (small) VSP_RC_LAUNCH(refine_cluster_small_kernel<double>)
                     else VSP_RC_LAUNCH(refine_cluster_kernel<double>)
                 }
 #undef VSP_RC_LAUNCH

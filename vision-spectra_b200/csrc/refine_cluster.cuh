@@ -38,9 +38,12 @@ __host__ __device__ inline int64_t refine_cluster_slot_doubles(int64_t K, int64_
 // shared memory (doubles): reduction scratch | dq eq [npad] | v y [Kpad] | part [kRcThreads] | u rowj [nlocpad] | X share
 // FUSED (K <= 32 RPL): the right update of step j-1 and the left reflector of step j are ONE sweep over the CTA's
 // columns (a column's rows live in RPL registers per lane between its load and its store) instead of two sweeps with
-// four passes.  n > 256 entry point only (n = 768: 14.8 -> 11.6 ms per matrix).  At 64 registers (n <= 256 entry point)
-// the sweep spills and the re-solve slowed from 2.25 to 2.35 ms; with y' folded in as well (FUSEY: per-warp partial
-// y' through shared memory) to 2.44 ms: RPL = 0 there.
+// four passes (n = 768: 14.8 -> 11.6 ms per matrix; n = 192 on the exclusive entry point: 1.5 -> 1.3 ms).  The entry
+// point that runs beside the bisection kernel does NOT take it (RPL = 0): at 64 registers the sweep spills (re-solve
+// 2.25 -> 2.35 ms); at 68..80 registers it is faster by itself, but every register it takes is a bisection CTA less on
+// its SM -- stage 3 of the Scenario-A sweep 2.25 -> 2.13 ms with 28 flagged matrices per step, 2.30 -> 2.44 ms with
+// the 36 of the bench's data (108 of 148 SMs host a re-solve CTA there); at 96: 2.43 ms either way.  With y' folded
+// in as well (FUSEY: per-warp partial y' through shared memory) it was slower everywhere it was tried.
 constexpr int kRcRplWide = 24;  // K <= 768
 __host__ __device__ inline size_t refine_cluster_ypw_doubles(bool shared_variant) {
     (void)shared_variant;

@@ -39,11 +39,14 @@ __host__ __device__ inline int64_t refine_cluster_slot_doubles(int64_t K, int64_
 // FUSED (K <= 32 RPL): the right update of step j-1 and the left reflector of step j are ONE sweep over the CTA's
 // columns (a column's rows live in RPL registers per lane between its load and its store) instead of two sweeps with
 // four passes (n = 768: 14.8 -> 11.6 ms per matrix; n = 192 on the exclusive entry point: 1.5 -> 1.3 ms).  The entry
-// point that runs beside the bisection kernel does NOT take it (RPL = 0): at 64 registers the sweep spills (re-solve
-// 2.25 -> 2.35 ms); at 68..80 registers it is faster by itself, but every register it takes is a bisection CTA less on
-// its SM -- stage 3 of the Scenario-A sweep 2.25 -> 2.13 ms with 28 flagged matrices per step, 2.30 -> 2.44 ms with
-// the 36 of the bench's data (108 of 148 SMs host a re-solve CTA there); at 96: 2.43 ms either way.  With y' folded
-// in as well (FUSEY: per-warp partial y' through shared memory) it was slower everywhere it was tried.
+// point that runs beside the bisection kernel takes it with an 80-register cap, together with a 64-register bisection
+// kernel: every register of the re-solve CTA is bisection work that does not fit on its SM (108 of 148 SMs host a
+// re-solve CTA with the bench's 36 flagged matrices).  Stage 3 of the Scenario-A sweep, 36 / 28 flagged matrices:
+//   re-solve 64 registers, three sweeps, bisection 80 registers   2.30 / 2.25 ms   (one sweep at 64: spills, 2.35)
+//   re-solve 72..80, one sweep, bisection 80                      2.44 / 2.13
+//   re-solve 80, one sweep, bisection 64                          2.23 / 2.11      <- this build
+//   re-solve 96                                                   2.43 either way
+// With y' folded in as well (FUSEY: per-warp partial y' through shared memory) it was slower everywhere it was tried.
 constexpr int kRcRplWide = 24;  // K <= 768
 __host__ __device__ inline size_t refine_cluster_ypw_doubles(bool shared_variant) {
     (void)shared_variant;
@@ -419,7 +422,7 @@ __device__ __forceinline__ void refine_cluster_body(const ItemDesc* __restrict__
 //   refine_cluster_kernel        n > 256: the re-solve is the long pole (29 ms per ViT-Base chunk against 2 ms of
 //                                bisection), all registers, default carve-out (the L2-resident shares like the L1);
 //   refine_cluster_shared_kernel n <= 256: runs BESIDE the bisection kernel, so it must leave room on its SMs: at most
-//                                64 registers (124 x 512 threads took an SM's whole register file) and, set by the
+//                                80 registers (124 x 512 threads took an SM's whole register file) and, set by the
 //                                host, the maximum shared-memory carve-out (with the default split no bisection CTA
 //                                fitted next to the 120 KB of a re-solve CTA).  Both were needed: stage 3 of the
 //                                Scenario-A sweep 2.65 -> 2.22 ms although the re-solve itself slows from 1.5 to 2.1 ms.
@@ -440,11 +443,11 @@ __global__ void __launch_bounds__(kRcThreads)
     refine_cluster_body<TIn, false, 8, false>(items, gate, pool, npad, Kpad, nloc_max, xs_cap, opts, sv_out, records, dist_out);
 }
 template <typename TIn>
-__global__ void __maxnreg__(64)
+__global__ void __maxnreg__(80)
     refine_cluster_shared_kernel(const ItemDesc* __restrict__ items, RefineGate gate, RefinePool pool, int npad, int Kpad,
                                  int nloc_max, int xs_cap, vsp_opts opts, double* __restrict__ sv_out,
                                  vsp_record* __restrict__ records, double* __restrict__ dist_out) {
-    refine_cluster_body<TIn, false, 0, false>(items, gate, pool, npad, Kpad, nloc_max, xs_cap, opts, sv_out, records, dist_out);
+    refine_cluster_body<TIn, false, 8, false>(items, gate, pool, npad, Kpad, nloc_max, xs_cap, opts, sv_out, records, dist_out);
 }
 
 #endif  // __CUDACC__

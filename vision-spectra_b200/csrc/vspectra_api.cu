@@ -515,8 +515,8 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
 
     // per-device attribute; cheap enough to set on every call (one process may drive several GPUs)
     VSP_CUDA(cudaFuncSetAttribute(tridiag_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    VSP_CUDA(cudaFuncSetAttribute(bisect_metrics_kernel<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    VSP_CUDA(cudaFuncSetAttribute(bisect_metrics_kernel<128, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    VSP_CUDA(cudaFuncSetAttribute(bisect_metrics_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VSP_CUDA(cudaFuncSetAttribute(bisect_metrics_kernel<128, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     VSP_CUDA(cudaFuncSetAttribute(bisect_metrics_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 
     auto mark = [&]() -> int {
@@ -738,7 +738,7 @@ static int execute_impl(vsp_plan* p, const void* const* d_ptrs, double* d_sv, vs
         }
         const int bthreads = bisect_threads(c.n);
         if (bthreads <= 128)
-            bisect_metrics_kernel<128, 6><<<c.count, bthreads, bisect_smem_bytes(c.npad), bst>>>(p->d_items, c.begin, ws, c.npad,
+            bisect_metrics_kernel<128, 8><<<c.count, bthreads, bisect_smem_bytes(c.npad), bst>>>(p->d_items, c.begin, ws, c.npad,
                                                                                                  p->opts, d_sv, d_records, d_dist);
         else
             bisect_metrics_kernel<1024, 1><<<c.count, bthreads, bisect_smem_bytes(c.npad), bst>>>(p->d_items, c.begin, ws, c.npad,

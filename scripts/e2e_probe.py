@@ -1,4 +1,4 @@
-"""e2e-only probe: times SweepRunner.run_host on the Scenario-A sweep (pinned host arenas), a few chunk schedules."""
+"""e2e-only probe: times SweepRunner.run_host on the Scenario-A sweep (pinned host arenas); CHUNK / LANES from the environment."""
 import os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -24,4 +24,4 @@ for _ in range(8):
     runner.run_host(arenas)
     ts.append(time.perf_counter() - t0)
 ts = np.array(ts) * 1e3
-print(f"chunk {chunk} lanes {lanes} head {os.environ.get('VSP_E2E_HEAD')} tail {os.environ.get('VSP_E2E_TAIL')}: ms median {np.median(ts):.2f} min {ts.min():.2f}  -> {nck * lay.matrices / np.median(ts) * 1e3:.0f} matrices/s; floor at 55 GB/s {host_block.numel() * 4 / 55e9 * 1e3:.2f} ms")
+print(f"chunk {chunk} lanes {lanes}: ms median {np.median(ts):.2f} min {ts.min():.2f}  -> {nck * lay.matrices / np.median(ts) * 1e3:.0f} matrices/s; floor at 55 GB/s {host_block.numel() * 4 / 55e9 * 1e3:.2f} ms")

@@ -45,7 +45,9 @@ def _ref_gram(m):
 def test_gram_matches_float64_matmul(dtype):
     g = torch.Generator(device="cuda").manual_seed(1)
     shapes = [(32, 32), (128, 32), (32, 128), (96, 96), (384, 96), (96, 384), (192, 192), (768, 192), (192, 768),
-              (7, 7), (9, 33), (257, 65), (200, 130), (1, 1), (100, 4), (300, 300)]
+              (7, 7), (9, 33), (257, 65), (200, 130), (1, 1), (100, 4), (300, 300),
+              # last 128-row tile of at most 64 rows (transposed-tile enumeration, gram_i8.cuh: I8Class::xt) and just above
+              (320, 320), (500, 448), (450, 450), (193, 700)]
     mats = [(torch.randn(s, generator=g, device="cuda", dtype=torch.float32) * 0.02).to(dtype) for s in shapes]
     # rows spanning 9 decades, denormals, an exact-zero row
     wide = torch.randn(64, 256, generator=g, device="cuda") * torch.logspace(-6, 3, 64, device="cuda")[:, None]

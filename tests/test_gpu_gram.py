@@ -65,6 +65,27 @@ def test_gram_matches_float64_matmul(dtype):
         assert np.array_equal(G, G.T)
 
 
+def test_gram_random_orders():
+    """Seeded sweep over Gram orders around the tile boundaries (64 / 128 / 192 / 256, multiples of 8 and not), both
+    orientations, short and long contractions: every tile enumeration, frame offset and store path of the int8 kernel."""
+    rng = np.random.default_rng(7)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    shapes = []
+    for n in list(rng.integers(57, 72, 4)) + list(rng.integers(120, 140, 6)) + list(rng.integers(185, 201, 6)) + list(
+            rng.integers(250, 330, 6)) + list(rng.integers(380, 460, 3)):
+        K = int(rng.choice([int(n), int(n) + 5, 2 * int(n), 777]))
+        K = max(K, int(n))
+        shapes.append((int(n), K) if rng.random() < 0.5 else (K, int(n)))
+    mats = [torch.randn(s, generator=g, device="cuda", dtype=torch.float32) * 0.02 for s in shapes]
+    got = _gram_via_abi(mats)
+    for m, G in zip(mats, got):
+        ref = _ref_gram(m)
+        dg = np.sqrt(np.maximum(np.diag(ref), 0))
+        err = np.max(np.abs(G - ref) / np.outer(dg, dg))
+        assert np.all(np.isfinite(G)) and err < 1e-13, (tuple(m.shape), err)
+        assert np.array_equal(G, G.T)
+
+
 def test_gram_views_and_nonfinite():
     g = torch.Generator(device="cuda").manual_seed(2)
     qkv = torch.randn(3 * 192, 192, generator=g, device="cuda") * 0.02

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256, 6)
     int* __restrict__ Eout = reinterpret_cast<int*>(wsb + cls.exp_off) + (int64_t)blockIdx.x * n;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ int sE[32];
-    __shared__ __align__(16) signed char sdig[kDigits][32][17 * 4];  // [plane][Gram row][17 words]: see the transposing branch
+    __shared__ __align__(16) signed char sdig[2][kDigits][32][17 * 4];  // [chunk parity][plane][Gram row][17 words]: see the transposing branch
     bool any_rounded = false;  // some Gram row of this block accumulated more than one quantum of rounding
 
     if (!it.trans) {
@@ -269,8 +269,10 @@ __global__ void __launch_bounds__(256, 6)
         double res2 = 0.0;  // this thread's share of Gram row i0 + lane
         // digits staged as 32-bit words (four consecutive k of one Gram row), row pitch 17 words: lanes (= Gram rows) fall
         // into different banks (the byte-granular staging at an 80-byte pitch ran at 4-way conflicts: ncu r01)
-        unsigned(*sw)[32][17] = reinterpret_cast<unsigned(*)[32][17]>(&sdig[0][0][0]);
+        // (two staging buffers, alternating by chunk: one barrier per chunk -- the buffer a chunk writes was last read two
+        // chunks ago, and every thread has passed the barrier in between)
         for (int k0 = 0; k0 < kp; k0 += 64) {
+            unsigned(*sw)[32][17] = reinterpret_cast<unsigned(*)[32][17]>(&sdig[(k0 >> 6) & 1][0][0][0]);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int kw = warp + 8 * j;  // word index inside the 64-byte chunk: k = k0 + 4 kw .. + 3
@@ -291,10 +293,10 @@ __global__ void __launch_bounds__(256, 6)
                 const int t = v >> 9, r = (v >> 4) & 31, c = v & 15;
                 if (i0 + r < n) *reinterpret_cast<unsigned*>(planes + ((int64_t)t * n + i0 + r) * kp + k0 + 4 * c) = sw[t][r][c];
             }
-            __syncthreads();
         }
-        // per Gram row: the eight warps' shares meet in shared memory (the digit staging buffer is free now)
-        float* sres = reinterpret_cast<float*>(&sdig[0][0][0]);  // [8][32]
+        __syncthreads();
+        // per Gram row: the eight warps' shares meet in shared memory (the digit staging buffers are free now)
+        float* sres = reinterpret_cast<float*>(&sdig[0][0][0][0]);  // [8][32]
         sres[warp * 32 + lane] = (float)res2;
         __syncthreads();
         if (warp == 0) {
